@@ -1,0 +1,143 @@
+"""Host-side replay of the reference's per-crop random draws -> crop parameter table.
+
+The reference draws its sampling / augmentation randomness on the host, per crop, from two generators
+(torch's default CPU generator and NumPy's global legacy RandomState), in a data-dependent order:
+
+  /root/reference/aphantasia/utils.py:222-228   rnd_size, rnd_offx, rnd_offy  (torch.rand / randn, [count])
+  /root/reference/aphantasia/utils.py:244       torch.rand(1) < macro         (per crop, always drawn)
+  /root/reference/aphantasia/utils.py:245-247   csize / offsetx / offsety     (fp32 tensor lerp, .int() trunc)
+  torchvision transforms.py:811,829-846         RandomPerspective: rand(1) < p, then 8x randint on hit
+  torchvision transforms.py:1727,1697-1714      RandomErasing: rand(1) < p, then <=10x (uniform_, uniform_), randint x2
+  /root/reference/aphantasia/transforms.py:75   np.random.choice(angles)      (NumPy global RNG)
+
+This module performs the *same calls in the same order* (so identical seeds give identical crops) and
+packs the result into a float32 table [count, CROP_PARAM_FLOATS] that one CUDA launch consumes
+(include/aphb200.h: aph_sample_fwd). No image data is touched here.
+"""
+import math
+
+import numpy as np
+import torch
+
+CROP_PARAM_FLOATS = 24
+# field offsets inside one table row (all stored as float32; integer fields are exact: |v| < 2^24)
+F_OFFY, F_OFFX, F_CSIZE, F_FLAGS = 0, 1, 2, 3
+F_PERSP = 4          # 8 floats a..h  (output -> input mapping, torchvision convention)
+F_ER_I, F_ER_J, F_ER_H, F_ER_W = 12, 13, 14, 15
+F_ROT = 16           # theta00, theta01, theta10, theta11 (inverse affine matrix, float32)
+F_ANGLE = 20         # degrees (informational)
+FLAG_PERSP, FLAG_ERASE, FLAG_ROT = 1, 2, 4
+
+# transform kinds understood by the fused sampler
+TF_NONE, TF_NORMALIZE, TF_FAST = 0, 1, 2
+
+FAST_ANGLES = list(range(-30, 30)) + 20 * [0]   # reference transforms.py:168
+PERSP_DISTORTION, PERSP_P = 0.33, 0.2           # reference transforms.py:166
+ERASE_P, ERASE_SCALE, ERASE_RATIO = 0.2, (0.02, 0.33), (0.3, 3.3)  # transforms.py:167 + torchvision defaults
+
+
+def perspective_coeffs(startpoints, endpoints):
+    """8 perspective coefficients, float64 least squares then cast to float32.
+    Same construction as torchvision functional.py:674-704 (what RandomPerspective executes)."""
+    a = torch.zeros(8, 8, dtype=torch.float64)
+    for i, (p1, p2) in enumerate(zip(endpoints, startpoints)):
+        a[2 * i, :] = torch.tensor([p1[0], p1[1], 1, 0, 0, 0, -p2[0] * p1[0], -p2[0] * p1[1]])
+        a[2 * i + 1, :] = torch.tensor([0, 0, 0, p1[0], p1[1], 1, -p2[1] * p1[0], -p2[1] * p1[1]])
+    b = torch.tensor(startpoints, dtype=torch.float64).view(8)
+    return torch.linalg.lstsq(a, b, driver='gels').solution.to(torch.float32).tolist()
+
+
+def inverse_rotation_matrix(angle):
+    """theta = [cos, sin, -sin, cos] of the inverse affine matrix for a pure rotation about (0,0)
+    (torchvision functional.py:1029-1052 with center=translate=shear=0, scale=1)."""
+    rot = math.radians(angle)
+    a = math.cos(rot); b = -math.sin(rot); c = math.sin(rot); d = math.cos(rot)
+    return [d, -b, -c, a]
+
+
+def draw_fast(row, size):
+    """Draws one crop's transforms_fast parameters into `row` (numpy float32 view), reference order."""
+    flags = 0
+    # RandomPerspective(0.33, p=0.2)
+    if torch.rand(1) < PERSP_P:
+        half = size // 2
+        d = int(PERSP_DISTORTION * half)
+        ri = lambda lo, hi: int(torch.randint(lo, hi, size=(1,)).item())
+        tl = [ri(0, d + 1), ri(0, d + 1)]
+        tr = [ri(size - d - 1, size), ri(0, d + 1)]
+        br = [ri(size - d - 1, size), ri(size - d - 1, size)]
+        bl = [ri(0, d + 1), ri(size - d - 1, size)]
+        start = [[0, 0], [size - 1, 0], [size - 1, size - 1], [0, size - 1]]
+        row[F_PERSP:F_PERSP + 8] = perspective_coeffs(start, [tl, tr, br, bl])
+        flags |= FLAG_PERSP
+    # RandomErasing(p=0.2), value=0
+    if torch.rand(1) < ERASE_P:
+        area = size * size
+        log_ratio = torch.log(torch.tensor(ERASE_RATIO))
+        for _ in range(10):
+            erase_area = area * torch.empty(1).uniform_(ERASE_SCALE[0], ERASE_SCALE[1]).item()
+            aspect = torch.exp(torch.empty(1).uniform_(log_ratio[0], log_ratio[1])).item()
+            h = int(round(math.sqrt(erase_area * aspect)))
+            w = int(round(math.sqrt(erase_area / aspect)))
+            if not (h < size and w < size):
+                continue
+            i = torch.randint(0, size - h + 1, size=(1,)).item()
+            j = torch.randint(0, size - w + 1, size=(1,)).item()
+            row[F_ER_I], row[F_ER_J], row[F_ER_H], row[F_ER_W] = i, j, h, w
+            flags |= FLAG_ERASE
+            break
+    # random_rotate_fast: always executed, even for angle 0
+    angle = float(np.random.choice(FAST_ANGLES))
+    row[F_ROT:F_ROT + 4] = inverse_rotation_matrix(angle)
+    row[F_ANGLE] = angle
+    flags |= FLAG_ROT
+    return flags
+
+
+def draw_crop_table(count, canvas_hw, size=224, kind=TF_FAST, align='uniform', macro=0., n_imgs=1):
+    """Replays slice_imgs' draws (reference utils.py:218-254) for `n_imgs` canvases of equal size.
+
+    Returns a list (one per input image) of float32 numpy tables [count, CROP_PARAM_FLOATS] and the
+    (pad_top, pad_left, padded_h, padded_w) of the wrap-padded sampling frame ('over*' aligns).
+    """
+    H, W = int(canvas_hw[0]), int(canvas_hw[1])
+    rnd_size = torch.rand(count)
+    if align == 'central':
+        rnd_offx = torch.clip(torch.randn(count) * 0.2 + 0.5, 0., 1.)
+        rnd_offy = torch.clip(torch.randn(count) * 0.2 + 0.5, 0., 1.)
+    else:
+        rnd_offx = torch.rand(count)
+        rnd_offy = torch.rand(count)
+    sz_max = torch.min(torch.tensor([H, W]))
+    if 'over' in align:
+        fh, fw = (2 * H, 2 * W) if align == 'overmax' else (int(1.5 * H), int(1.5 * W))
+    else:
+        fh, fw = H, W
+    pad_top, pad_left = (fh - H) // 2, (fw - W) // 2      # pad_up_to 'centr' (utils.py:183-184)
+
+    lerp = lambda x, a, b: x * (b - a) + a                # utils.py:219-220 (`map`)
+    tables = []
+    for _ in range(n_imgs):
+        tab = np.zeros((count, CROP_PARAM_FLOATS), dtype=np.float32)
+        for c in range(count):
+            sz_min = 0.9 * sz_max if torch.rand(1) < macro else size
+            csize = lerp(rnd_size[c], sz_min, sz_max).int()
+            offx = lerp(rnd_offx[c], 0, fw - csize).int()
+            offy = lerp(rnd_offy[c], 0, fh - csize).int()
+            row = tab[c]
+            row[F_OFFY], row[F_OFFX], row[F_CSIZE] = int(offy), int(offx), int(csize)
+            row[F_ROT:F_ROT + 4] = (1., 0., 0., 1.)
+            flags = 0
+            if kind == TF_FAST:
+                flags = draw_fast(row, size)
+            row[F_FLAGS] = flags
+        tables.append(tab)
+    return tables, (pad_top, pad_left, fh, fw)
+
+
+def shard_range(count, rank, world):
+    """Contiguous, balanced shard [lo, hi) of the crop index for `rank` of `world`
+    (190 over 8 -> 24x6 + 23x2; 87 over 4 -> 22,22,22,21)."""
+    base, rem = divmod(count, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
