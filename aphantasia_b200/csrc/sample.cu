@@ -1,0 +1,275 @@
+// sample.cu -- fused multi-crop sampler + transforms_fast, forward and backward (fp32, L2/HBM-bound).
+//
+// Replaces the per-crop Python loop of /root/reference/aphantasia/utils.py:243-253 (slice_imgs) with
+// transforms_fast (/root/reference/aphantasia/transforms.py:165-170) applied per crop:
+//   1. cut = canvas[oy:oy+cs, ox:ox+cs]; bicubic (A=-0.75, align_corners=True, taps clamped to the crop)
+//      resize to size x size                                       (utils.py:248-249)
+//   2. RandomPerspective hit: bilinear grid_sample(zeros, align_corners=False) of [img; ones],
+//      out = img_s * mask_s                                        (torchvision _functional_tensor.py:545-576,672-698)
+//   3. RandomErasing hit: rectangle -> 0                           (_functional_tensor.py:931-938)
+//   4. rotate (always, even 0 deg): affine grid + the same masked grid_sample (transforms.py:80,
+//      _functional_tensor.py:579-618)
+//   5. (x - mean) / std with the CLIP constants                    (transforms.py:106-108)
+// The stages are SEQUENTIAL resamplings of intermediate size x size images. One CTA owns one
+// (crop, channel): stage 1 is materialised in shared memory (size^2 fp32 = 196 KB at 224), stages 2-5
+// are evaluated by exact tap composition on top of it (rotate tap -> erase test -> perspective taps),
+// so every intermediate is the reference's intermediate and nothing but the packed batch is written.
+//
+// Backward mirrors it: rotate/perspective adjoints scatter into a shared-memory gradient image
+// (shared atomics), then the bicubic adjoint scatters into the canvas gradient (global red.add).
+#include "aph_common.cuh"
+
+namespace aph {
+
+constexpr float kCubicA = -0.75f;
+__device__ __forceinline__ float cubic1(float x) { return ((kCubicA + 2.f) * x - (kCubicA + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x) { return ((kCubicA * x - 5.f * kCubicA) * x + 8.f * kCubicA) * x - 4.f * kCubicA; }
+
+struct CropParams {
+  int oy, ox, cs, flags;
+  float pc[8];
+  int ei, ej, eh, ew;
+  float r00, r01, r10, r11;
+};
+
+__device__ __forceinline__ CropParams load_params(const float* __restrict__ row) {
+  CropParams p;
+  p.oy = (int)row[APH_F_OFFY]; p.ox = (int)row[APH_F_OFFX]; p.cs = (int)row[APH_F_CSIZE]; p.flags = (int)row[APH_F_FLAGS];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p.pc[i] = row[APH_F_PERSP + i];
+  p.ei = (int)row[APH_F_ER_I]; p.ej = (int)row[APH_F_ER_J]; p.eh = (int)row[APH_F_ER_H]; p.ew = (int)row[APH_F_ER_W];
+  p.r00 = row[APH_F_ROT]; p.r01 = row[APH_F_ROT + 1]; p.r10 = row[APH_F_ROT + 2]; p.r11 = row[APH_F_ROT + 3];
+  return p;
+}
+
+// bicubic source index + 4 weights for output index i (align_corners=True)
+__device__ __forceinline__ void cubic_taps(int i, float scale, int cs, int idx[4], float w[4]) {
+  const float real = scale * (float)i;
+  int i0 = (int)floorf(real);
+  i0 = min(i0, cs - 1);
+  float t = fminf(fmaxf(real - (float)i0, 0.f), 1.f);
+  w[0] = cubic2(t + 1.f); w[1] = cubic1(t); w[2] = cubic1(1.f - t); w[3] = cubic2(2.f - t);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) idx[a] = max(min(i0 - 1 + a, cs - 1), 0);
+}
+
+// bilinear grid_sample taps (align_corners=False, zeros padding) for normalised coords (gx, gy).
+struct Bilin { int x0, y0; float w00, w01, w10, w11; };   // wYX; taps (y0,x0) (y0,x0+1) (y0+1,x0) (y0+1,x0+1)
+__device__ __forceinline__ Bilin bilin_taps(float gx, float gy, int size) {
+  const float ix = ((gx + 1.f) * (float)size - 1.f) * 0.5f;
+  const float iy = ((gy + 1.f) * (float)size - 1.f) * 0.5f;
+  const float fx = floorf(ix), fy = floorf(iy);
+  Bilin b;
+  b.x0 = (int)fx; b.y0 = (int)fy;
+  const float tx = ix - fx, ty = iy - fy;
+  b.w00 = (1.f - tx) * (1.f - ty); b.w01 = tx * (1.f - ty);
+  b.w10 = (1.f - tx) * ty;         b.w11 = tx * ty;
+  const bool xin0 = b.x0 >= 0 && b.x0 < size, xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < size;
+  const bool yin0 = b.y0 >= 0 && b.y0 < size, yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < size;
+  if (!(xin0 && yin0)) b.w00 = 0.f;
+  if (!(xin1 && yin0)) b.w01 = 0.f;
+  if (!(xin0 && yin1)) b.w10 = 0.f;
+  if (!(xin1 && yin1)) b.w11 = 0.f;
+  return b;
+}
+
+__device__ __forceinline__ Bilin rot_taps(const CropParams& p, int i, int j, int size) {
+  const float half = 0.5f * (float)size;
+  const float bx = (float)j + 0.5f - half, by = (float)i + 0.5f - half;
+  const float gx = bx * (p.r00 / half) + by * (p.r01 / half);
+  const float gy = bx * (p.r10 / half) + by * (p.r11 / half);
+  return bilin_taps(gx, gy, size);
+}
+
+__device__ __forceinline__ Bilin persp_taps(const CropParams& p, int y, int x, int size) {
+  const float half = 0.5f * (float)size;
+  const float bx = (float)x + 0.5f, by = (float)y + 0.5f;
+  const float n1x = bx * (p.pc[0] / half) + by * (p.pc[1] / half) + (p.pc[2] / half);
+  const float n1y = bx * (p.pc[3] / half) + by * (p.pc[4] / half) + (p.pc[5] / half);
+  const float den = bx * p.pc[6] + by * p.pc[7] + 1.f;
+  return bilin_taps(n1x / den - 1.f, n1y / den - 1.f, size);
+}
+
+__device__ __forceinline__ float tap_dot(const float* __restrict__ A, const Bilin& b, int size) {
+  float v = 0.f;
+  if (b.w00 != 0.f) v += b.w00 * A[b.y0 * size + b.x0];
+  if (b.w01 != 0.f) v += b.w01 * A[b.y0 * size + b.x0 + 1];
+  if (b.w10 != 0.f) v += b.w10 * A[(b.y0 + 1) * size + b.x0];
+  if (b.w11 != 0.f) v += b.w11 * A[(b.y0 + 1) * size + b.x0 + 1];
+  return v;
+}
+
+// value of the post-perspective, post-erase image B at integer pixel (y, x)
+__device__ __forceinline__ float stageB(const float* __restrict__ A, const CropParams& p, int y, int x, int size) {
+  if ((p.flags & APH_FLAG_ERASE) && y >= p.ei && y < p.ei + p.eh && x >= p.ej && x < p.ej + p.ew) return 0.f;
+  if (p.flags & APH_FLAG_PERSP) {
+    const Bilin b = persp_taps(p, y, x, size);
+    const float mask = b.w00 + b.w01 + b.w10 + b.w11;
+    return tap_dot(A, b, size) * mask;
+  }
+  return A[y * size + x];
+}
+
+__constant__ float c_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+__constant__ float c_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+
+__global__ void __launch_bounds__(1024, 1)
+k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pad_left, const float* __restrict__ table,
+             int size, int kind, float* __restrict__ out) {
+  extern __shared__ float A[];
+  const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
+  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  const float* cch = canvas + (size_t)ch * H * W;
+  const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
+  const int n = size * size;
+  // ---- stage 1: bicubic resize into shared memory
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int i = idx / size, j = idx - i * size;
+    int iy[4], ix[4]; float wy[4], wx[4];
+    cubic_taps(i, scale, p.cs, iy, wy);
+    cubic_taps(j, scale, p.cs, ix, wx);
+    int cx[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { int x = p.ox + ix[b] - pad_left; x %= W; if (x < 0) x += W; cx[b] = x; }
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int y = p.oy + iy[a] - pad_top; y %= H; if (y < 0) y += H;
+      const float* r = cch + (size_t)y * W;
+      const float rowv = wx[0] * __ldg(r + cx[0]) + wx[1] * __ldg(r + cx[1]) + wx[2] * __ldg(r + cx[2]) + wx[3] * __ldg(r + cx[3]);
+      acc += wy[a] * rowv;
+    }
+    A[idx] = acc;
+  }
+  __syncthreads();
+  // ---- stages 2-5 by tap composition
+  float* o = out + ((size_t)crop * 3 + ch) * n;
+  const float mean = c_mean[ch], sd = c_std[ch];
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    float v;
+    if (kind == APH_TF_FAST) {
+      const int i = idx / size, j = idx - i * size;
+      const Bilin b = rot_taps(p, i, j, size);
+      const float mask = b.w00 + b.w01 + b.w10 + b.w11;
+      float s = 0.f;
+      if (b.w00 != 0.f) s += b.w00 * stageB(A, p, b.y0, b.x0, size);
+      if (b.w01 != 0.f) s += b.w01 * stageB(A, p, b.y0, b.x0 + 1, size);
+      if (b.w10 != 0.f) s += b.w10 * stageB(A, p, b.y0 + 1, b.x0, size);
+      if (b.w11 != 0.f) s += b.w11 * stageB(A, p, b.y0 + 1, b.x0 + 1, size);
+      v = s * mask;
+    } else {
+      v = A[idx];
+    }
+    if (kind != APH_TF_NONE) v = (v - mean) / sd;
+    o[idx] = v;
+  }
+}
+
+__device__ __forceinline__ void scatterB(float* __restrict__ gA, const CropParams& p, int y, int x, int size, float g) {
+  if ((p.flags & APH_FLAG_ERASE) && y >= p.ei && y < p.ei + p.eh && x >= p.ej && x < p.ej + p.ew) return;
+  if (p.flags & APH_FLAG_PERSP) {
+    const Bilin b = persp_taps(p, y, x, size);
+    const float gm = g * (b.w00 + b.w01 + b.w10 + b.w11);
+    if (b.w00 != 0.f) atomicAdd(&gA[b.y0 * size + b.x0], gm * b.w00);
+    if (b.w01 != 0.f) atomicAdd(&gA[b.y0 * size + b.x0 + 1], gm * b.w01);
+    if (b.w10 != 0.f) atomicAdd(&gA[(b.y0 + 1) * size + b.x0], gm * b.w10);
+    if (b.w11 != 0.f) atomicAdd(&gA[(b.y0 + 1) * size + b.x0 + 1], gm * b.w11);
+  } else {
+    atomicAdd(&gA[y * size + x], g);
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int pad_left, const float* __restrict__ table,
+             int size, int kind, float* __restrict__ grad_canvas) {
+  extern __shared__ float gA[];
+  const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
+  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  const int n = size * size;
+  const float* go = grad_out + ((size_t)crop * 3 + ch) * n;
+  const float inv_sd = (kind != APH_TF_NONE) ? 1.f / c_std[ch] : 1.f;
+  if (kind == APH_TF_FAST) {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = 0.f;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+      const int i = idx / size, j = idx - i * size;
+      const Bilin b = rot_taps(p, i, j, size);
+      const float g = go[idx] / c_std[ch] * (b.w00 + b.w01 + b.w10 + b.w11);
+      if (g == 0.f) continue;
+      if (b.w00 != 0.f) scatterB(gA, p, b.y0, b.x0, size, g * b.w00);
+      if (b.w01 != 0.f) scatterB(gA, p, b.y0, b.x0 + 1, size, g * b.w01);
+      if (b.w10 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0, size, g * b.w10);
+      if (b.w11 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0 + 1, size, g * b.w11);
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = go[idx] * inv_sd;
+  }
+  __syncthreads();
+  // ---- bicubic adjoint: scatter the 16 taps into the canvas gradient
+  float* gc = grad_canvas + (size_t)ch * H * W;
+  const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const float g = gA[idx];
+    if (g == 0.f) continue;
+    const int i = idx / size, j = idx - i * size;
+    int iy[4], ix[4]; float wy[4], wx[4];
+    cubic_taps(i, scale, p.cs, iy, wy);
+    cubic_taps(j, scale, p.cs, ix, wx);
+    int cx[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { int x = p.ox + ix[b] - pad_left; x %= W; if (x < 0) x += W; cx[b] = x; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int y = p.oy + iy[a] - pad_top; y %= H; if (y < 0) y += H;
+      float* r = gc + (size_t)y * W;
+      const float gy = g * wy[a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) atomicAdd(r + cx[b], gy * wx[b]);
+    }
+  }
+}
+
+}  // namespace aph
+
+using namespace aph;
+
+static int check_sample_args(const char* who, int H, int W, int S, int size, int kind) {
+  APH_REQUIRE(H > 0 && W > 0 && S >= 0 && size > 0, "%s: bad shape H=%d W=%d S=%d size=%d", who, H, W, S, size);
+  APH_REQUIRE((size_t)size * size * sizeof(float) <= 227 * 1024, "%s: size=%d does not fit one CTA's shared memory (max 238)", who, size);
+  APH_REQUIRE(kind >= APH_TF_NONE && kind <= APH_TF_FAST, "%s: unknown transform kind %d", who, kind);
+  return 0;
+}
+
+extern "C" int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, int pad_left, const float* table, int S,
+                              int size, int kind, float* out, void* stream) {
+  if (int e = check_sample_args("aph_sample_fwd", H, W, S, size, kind)) return e;
+  if (S == 0) return 0;
+  APH_REQUIRE(canvas && table && out, "aph_sample_fwd: null pointer");
+  const size_t smem = (size_t)size * size * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    APH_CUDA_OK(cudaFuncSetAttribute(k_sample_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  k_sample_fwd<<<S * 3, 1024, smem, (cudaStream_t)stream>>>(canvas, H, W, pad_top, pad_left, table, size, kind, out);
+  APH_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, int pad_left, const float* table, int S,
+                              int size, int kind, float* grad_canvas, void* stream) {
+  if (int e = check_sample_args("aph_sample_bwd", H, W, S, size, kind)) return e;
+  APH_REQUIRE(grad_canvas, "aph_sample_bwd: null grad_canvas");
+  APH_CUDA_OK(cudaMemsetAsync(grad_canvas, 0, (size_t)3 * H * W * sizeof(float), (cudaStream_t)stream));
+  if (S == 0) return 0;
+  APH_REQUIRE(grad_out && table, "aph_sample_bwd: null pointer");
+  const size_t smem = (size_t)size * size * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    APH_CUDA_OK(cudaFuncSetAttribute(k_sample_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  k_sample_bwd<<<S * 3, 1024, smem, (cudaStream_t)stream>>>(grad_out, H, W, pad_top, pad_left, table, size, kind, grad_canvas);
+  APH_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,323 @@
+// tc_gemm.cuh -- the tcgen05 / TMA / TMEM GEMM of the CLIP ViT encoder (sm_100a).
+//
+//   C[M,N] = A[M,K] . B[N,K]^T      A, B bf16 row-major (K contiguous = "K-major"), fp32 accumulate in TMEM.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0 (1 lane)  TMA producer : cp.async.bulk.tensor.2d -> 128B-swizzled smem stages, mbarrier complete_tx
+//   warp 1 (1 lane)  MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BLOCK_N x K=16 per instruction,
+//                                   tcgen05.commit releases smem stages / publishes the accumulator
+//   warp 2           TMEM allocator (2 accumulator stages x BLOCK_N columns)
+//   warps 4-7        epilogue     : tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+// Fused epilogues (struct GemmEpi): +bias, QuickGELU (saving the pre-activation), x gelu'(h) for the MLP
+// backward, +fp32 residual, fp32 and/or bf16 outputs, and an NCHW "un-patchify" store for the patch-embed
+// data gradient. Rows >= M are zero-filled by TMA on load and masked on store.
+#pragma once
+#include "aph_common.cuh"
+#include <cuda.h>
+
+namespace aph {
+
+typedef __nv_bfloat16 bf16;
+
+struct GemmEpi {
+  const float* bias = nullptr;     // [N]
+  const float* resid = nullptr;    // fp32 [M, N], added last
+  const bf16* gelu_in = nullptr;   // bf16 [M, N]: acc *= quickgelu'(gelu_in)
+  float* out_f32 = nullptr;        // fp32 [M, N] (or NCHW images when unpatch_p > 0)
+  bf16* out_bf16 = nullptr;        // bf16 [M, N]
+  bf16* out_pre = nullptr;         // bf16 [M, N] pre-activation (acc + bias), saved for backward
+  int act = 0;                     // 1 = QuickGELU x*sigmoid(1.702x)
+  int unpatch_p = 0;               // >0: out_f32 is [S,3,R,R]; row = s*g*g + gy*g + gx, col = c*p*p + py*p + px
+  int unpatch_g = 0;
+};
+
+struct GemmShape { int M, N, K; };
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;       // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int GEMM_UK = 16;       // K per tcgen05.mma (kind::f16)
+constexpr int GEMM_THREADS = 256;
+
+// ---- raw PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2-D tile load: coordinates (x = element index along K, y = row)
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = accumulator row)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO). sm_100 descriptor version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                          // layout type: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float quickgelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float quickgelu_grad(float x) {
+  const float s = 1.f / (1.f + __expf(-1.702f * x));
+  return s * (1.f + 1.702f * x * (1.f - s));
+}
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape shp, GemmEpi epi) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (shp.M + GEMM_BM - 1) / GEMM_BM, n_tiles = shp.N / BN;
+  const int num_tiles = m_tiles * n_tiles, k_blocks = shp.K / GEMM_BK;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          tma_load_2d(sa, &map_a, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(sa + L::A_BYTES, &map_b, &full_bar[s], kb * GEMM_BK, n_blk * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(BN);
+      uint32_t it = 0, tile_iter = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+        const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph_ ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / GEMM_UK; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (>>4) address field
+            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[s]);                   // smem stage free once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);   // accumulator complete
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31
+    const int q = warp & 3;
+    uint32_t tile_iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aph_);
+      tc_fence_after();
+      const int m = m_blk * GEMM_BM + q * 32 + lane;
+      const bool valid = m < shp.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_wait_ld();
+        if (c == BN / 32 - 1) {          // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (!valid) continue;
+        const int col0 = n_blk * BN + c * 32;
+        const size_t rowoff = (size_t)m * shp.N + col0;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (epi.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + i));
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+          }
+        }
+        if (epi.out_pre) {
+          uint4* o = reinterpret_cast<uint4*>(epi.out_pre + rowoff);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]), p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+            uint4 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+            u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+            o[i / 8] = u;
+          }
+        }
+        if (epi.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = quickgelu(v[i]);
+        }
+        if (epi.gelu_in) {
+          const uint4* hp = reinterpret_cast<const uint4*>(epi.gelu_in + rowoff);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const uint4 u = __ldg(hp + i / 8);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 h = __bfloat1622float2(h2[j]);
+              v[i + 2 * j] *= quickgelu_grad(h.x); v[i + 2 * j + 1] *= quickgelu_grad(h.y);
+            }
+          }
+        }
+        if (epi.resid) {
+          const float4* rp = reinterpret_cast<const float4*>(epi.resid + rowoff);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(rp + i / 4);
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+          }
+        }
+        if (epi.out_f32) {
+          if (epi.unpatch_p > 0) {
+            const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
+            const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const int col = col0 + i, ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
+              float* o = epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px;
+              *reinterpret_cast<float4*>(o) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+          } else {
+            float4* o = reinterpret_cast<float4*>(epi.out_f32 + rowoff);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) o[i / 4] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+        if (epi.out_bf16) {
+          uint4* o = reinterpret_cast<uint4*>(epi.out_bf16 + rowoff);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]), p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+            uint4 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+            u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+            o[i / 8] = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+// 2-D bf16 tensor map: tensor [rows, K] row-major, box [box_rows, 64] with 128B swizzle.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int K, int box_rows);
+// Launches the GEMM on `st`. A: [M,K], B: [N,K] device bf16. Requires K % 64 == 0, N % 128 == 0.
+int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st);
+
+}  // namespace aph

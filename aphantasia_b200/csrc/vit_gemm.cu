@@ -1,0 +1,72 @@
+// vit_gemm.cu -- host side of the tcgen05 GEMM (tensor-map encoding, launch) + the exported test entry.
+#include "tc_gemm.cuh"
+#include <mutex>
+
+namespace aph {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int K, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  APH_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  APH_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && K % 8 == 0, "tensor map: base/stride not 16-byte aligned");
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  APH_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: CUresult %d (rows=%d K=%d box_rows=%d)", (int)r, rows, K, box_rows);
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st) {
+  using L = GemmSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  CUtensorMap ma, mb;
+  if (int e = make_tmap_bf16(&ma, A, shp.M, shp.K, GEMM_BM)) return e;
+  if (int e = make_tmap_bf16(&mb, B, shp.N, shp.K, BN)) return e;
+  const int tiles = ((shp.M + GEMM_BM - 1) / GEMM_BM) * (shp.N / BN);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  k_gemm_bf16_tn<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, shp, epi);
+  APH_LAUNCH_OK();
+  return 0;
+}
+
+int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st) {
+  APH_REQUIRE(A && B && shp.M > 0, "gemm: null operand or empty M");
+  APH_REQUIRE(shp.K % GEMM_BK == 0 && shp.K > 0, "gemm: K=%d must be a positive multiple of %d", shp.K, GEMM_BK);
+  APH_REQUIRE(shp.N % 128 == 0 && shp.N > 0, "gemm: N=%d must be a positive multiple of 128", shp.N);
+  return launch_cfg<128, 6>(A, B, shp, epi, st);
+}
+
+}  // namespace aph
+
+using namespace aph;
+
+extern "C" int aph_gemm_bf16_tn(const void* A, const void* B, float* C, int M, int N, int K, void* stream) {
+  APH_REQUIRE(C != nullptr, "aph_gemm_bf16_tn: null output");
+  GemmEpi epi;
+  epi.out_f32 = C;
+  return launch_gemm(A, B, GemmShape{M, N, K}, epi, (cudaStream_t)stream);
+}

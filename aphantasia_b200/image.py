@@ -1,0 +1,170 @@
+"""Image parameterisations -- drop-in for /root/reference/aphantasia/image.py (hot-path entry points).
+
+fft_image / to_valid_rgb keep the reference's signatures and return types (image.py:152-177, 14-29); the
+arithmetic runs in libaphb200.so (csrc/synth_fft.cu) through torch.autograd.Function wrappers so that
+`loss.backward()` deposits `params[0].grad` exactly as the reference's autograd does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _dist
+from ._lib import check, lib, require_cuda, stream_ptr
+
+
+def _color_matrix_host(colors):
+    """Mn[d][c] such that out_d = sum_c Mn[d][c] * img_c  (image.py:15-22: einsum('nchw,cd->ndhw', img, M.T))."""
+    m = torch.tensor([[0.26, 0.09, 0.02], [0.27, 0.00, -0.05], [0.27, -0.09, 0.03]])
+    m = m / torch.tensor([colors, 1., 1.])
+    m = m / m.norm(dim=0).max()
+    # colcorr_t = m.T ; out[d] = sum_c img[c] * colcorr_t[c, d] = sum_c m[d, c] * img[c]
+    return (C.c_float * 9)(*[float(v) for v in m.reshape(-1)])
+
+
+def rfft2d_freqs(h, w):
+    """image.py:122-128."""
+    fy = np.fft.fftfreq(h)[:, None]
+    w2 = (w + 1) // 2 if w % 2 == 1 else w // 2 + 1
+    fx = np.fft.fftfreq(w)[:w2]
+    return np.sqrt(fx * fx + fy * fy)
+
+
+class _SynthFFT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, params, gen, shift, contrast, colmat, sigmoid):
+        require_cuda(params, 'spectrum parameters')
+        h, w = gen.h, gen.w
+        p = params.detach().contiguous().float()
+        x_raw = torch.empty(3, h, w, device=p.device, dtype=torch.float32)
+        out = torch.empty(1, 3, h, w, device=p.device, dtype=torch.float32)
+        stats = torch.empty(4, device=p.device, dtype=torch.float64)
+        mode, sh = 0, None
+        if shift is not None:
+            sh = shift.detach().to(p.device, torch.float32).contiguous()
+            if sh.numel() == h * gen.wh:
+                mode = 1
+            elif sh.numel() == 3 * h * gen.wh * 2:
+                mode = 2
+            else:
+                raise ValueError('fft_image: unsupported shift shape %s' % (tuple(shift.shape),))
+        check(lib().aph_synth_fft_fwd(gen.plan, p.data_ptr(), gen.scale.data_ptr(), sh.data_ptr() if sh is not None else None, mode,
+                                      float(contrast), colmat, int(sigmoid), x_raw.data_ptr(), stats.data_ptr(), out.data_ptr(),
+                                      stream_ptr()), 'aph_synth_fft_fwd')
+        ctx.gen, ctx.contrast, ctx.colmat, ctx.sigmoid = gen, float(contrast), colmat, int(sigmoid)
+        ctx.save_for_backward(x_raw, stats, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x_raw, stats, out = ctx.saved_tensors
+        gen = ctx.gen
+        g = grad_out.contiguous().float()
+        gp = torch.empty(1, 3, gen.h, gen.wh, 2, device=g.device, dtype=torch.float32)
+        check(lib().aph_synth_fft_bwd(gen.plan, g.data_ptr(), out.data_ptr(), x_raw.data_ptr(), stats.data_ptr(), gen.scale.data_ptr(),
+                                      ctx.contrast, ctx.colmat, ctx.sigmoid, gp.data_ptr(), stream_ptr()), 'aph_synth_fft_bwd')
+        return gp, None, None, None, None, None
+
+
+class FFTImage:
+    """The `image_f` closure of fft_image (image.py:164-175) as a callable object, so to_valid_rgb can fuse into it."""
+
+    def __init__(self, params, h, w, decay_power):
+        self.params, self.h, self.w, self.wh = params, h, w, w // 2 + 1
+        freqs = rfft2d_freqs(h, w)
+        scale = 1. / np.maximum(freqs, 4. / max(h, w)) ** decay_power      # image.py:159-161 (float64 on the host)
+        scale *= np.sqrt(h * w)
+        self.scale = torch.tensor(scale).float().contiguous().cuda()
+        plan = C.c_void_p()
+        check(lib().aph_fft_plan_create(C.byref(plan), h, w), 'aph_fft_plan_create')
+        self.plan = plan
+
+    def __del__(self):
+        try:
+            if getattr(self, 'plan', None):
+                lib().aph_fft_plan_destroy(self.plan)
+        except Exception:
+            pass
+
+    def fused(self, shift, contrast, colmat, sigmoid):
+        return _SynthFFT.apply(self.params, self, shift, contrast, colmat, sigmoid)
+
+    def __call__(self, shift=None, contrast=1., *noargs, **nokwargs):
+        return self.fused(shift, contrast, None, False)
+
+
+def resume_fft(resume=None, shape=None, decay=None, colors=1.6, sd=0.01):
+    """image.py:130-150. Image-file resume (img2fft) is init-time and out of scope; .pt / tensor resume is kept."""
+    size = None
+    if resume is None:
+        params_shape = [*shape[:3], shape[3] // 2 + 1, 2]
+        params = 0.01 * torch.randn(*params_shape)
+        if _dist.world() > 1:                      # every rank must start from rank 0's draw
+            params = params.cuda(); torch.distributed.broadcast(params, 0)
+        params = params.cuda()
+    elif isinstance(resume, str):
+        if os.path.isfile(resume):
+            if os.path.splitext(resume)[1].lower()[1:] in ['jpg', 'png', 'tif', 'bmp']:
+                raise NotImplementedError('aphantasia_b200: resuming from an image file (img2fft) is not on the B200 hot path')
+            params = torch.load(resume)
+            if isinstance(params, list): params = params[0]
+            params = params.detach().cuda()
+            params *= sd
+        else:
+            print(' Snapshot not found:', resume); exit()
+    else:
+        if isinstance(resume, list): resume = resume[0]
+        params = resume.cuda()
+    return params, size
+
+
+def fft_image(shape, sd=0.01, decay_power=1.0, resume=None):
+    """Drop-in for image.py:152-177: returns ([spectrum_param], image_f, size)."""
+    _dist.init()
+    params, size = resume_fft(resume, shape, decay_power, sd=sd)
+    spectrum_real_imag_t = params.requires_grad_(True)
+    if size is not None: shape[2:] = size
+    [h, w] = list(shape[2:])
+    return [spectrum_real_imag_t], FFTImage(spectrum_real_imag_t, h, w, decay_power), size
+
+
+class _ValidRGB(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, colmat):
+        require_cuda(img, 'image')
+        x = img.detach().contiguous().float()
+        assert x.shape[0] == 1 and x.shape[1] == 3, 'to_valid_rgb expects [1,3,H,W]'
+        out = torch.empty_like(x)
+        check(lib().aph_valid_rgb_fwd(x.data_ptr(), x.shape[2] * x.shape[3], colmat, out.data_ptr(), stream_ptr()), 'aph_valid_rgb_fwd')
+        ctx.colmat = colmat
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out, = ctx.saved_tensors
+        g = g.contiguous().float()
+        gi = torch.empty_like(out)
+        check(lib().aph_valid_rgb_bwd(g.data_ptr(), out.data_ptr(), out.shape[2] * out.shape[3], ctx.colmat, gi.data_ptr(), stream_ptr()),
+              'aph_valid_rgb_bwd')
+        return gi, None
+
+
+def to_valid_rgb(image_f, colors=1., decorrelate=True):
+    """Drop-in for image.py:14-29. Fuses colour decorrelation + sigmoid into the synthesis kernel when
+    `image_f` is one of ours; otherwise applies the stand-alone kernel to whatever image_f returns."""
+    colmat = _color_matrix_host(colors) if decorrelate else None
+
+    def inner(*args, **kwargs):
+        if isinstance(image_f, FFTImage):
+            shift = args[0] if len(args) > 0 else kwargs.get('shift', None)
+            contrast = args[1] if len(args) > 1 else kwargs.get('contrast', 1.)
+            return image_f.fused(shift, contrast, colmat, True)
+        return _ValidRGB.apply(image_f(*args, **kwargs), colmat)
+    return inner
+
+
+def dwt_image(shape, wave='coif2', sharp=0.3, colors=1., resume=None):
+    """image.py:61-71 (DWT parameterisation, BASELINE config 3). Not built yet in this round."""
+    raise NotImplementedError('aphantasia_b200: dwt_image (SURVEY.md section 8a row a4) is not implemented yet; use FFT (default)')

@@ -1,0 +1,224 @@
+"""Sampler, loss and helper names -- drop-in for /root/reference/aphantasia/utils.py.
+
+slice_imgs (utils.py:218-254) and sim_func (utils.py:276-295) are the hot-path entry points: the host
+replays the reference's RNG order into a parameter table (_rng.py) and one fused CUDA launch does the rest
+(csrc/sample.cu, csrc/loss.cu). The remaining names are the thin IO helpers clip_fft.py imports.
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _dist, _rng
+from ._lib import check, lib, require_cuda, stream_ptr
+
+
+# ---------------------------------------------------------------------------------------------- sampler
+class _SliceImgs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, canvas, table_dev, meta):
+        H, W, pad_top, pad_left, S, size, kind, scale = meta
+        x = canvas.detach().contiguous().float()
+        out = torch.empty(S, 3, size, size, device=x.device, dtype=torch.float32)
+        check(lib().aph_sample_fwd(x.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, out.data_ptr(),
+                                   stream_ptr()), 'aph_sample_fwd')
+        ctx.meta = meta
+        ctx.save_for_backward(table_dev)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        table_dev, = ctx.saved_tensors
+        H, W, pad_top, pad_left, S, size, kind, scale = ctx.meta
+        g = grad_out.contiguous().float()
+        gc = torch.empty(1, 3, H, W, device=g.device, dtype=torch.float32)
+        check(lib().aph_sample_bwd(g.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, gc.data_ptr(),
+                                   stream_ptr()), 'aph_sample_bwd')
+        if _dist.world() > 1:
+            # each rank's loss is a mean over its own shard: weight by S_local/S_total, then sum over ranks
+            gc.mul_(scale)
+            _dist.all_reduce_sum_(gc)
+        return gc, None, None
+
+
+def _transform_kind(transform):
+    if transform is None:
+        return _rng.TF_NONE
+    kind = getattr(transform, 'kind', None)
+    if kind is None:
+        raise NotImplementedError('aphantasia_b200.slice_imgs: only transform=None, transforms.normalize() and '
+                                  'transforms.transforms_fast run in the fused sampler (got %r)' % (transform,))
+    return kind
+
+
+_pinned = {}
+
+
+def _table_to_device(tab, device):
+    """H2D of the per-step crop table through a reused pinned staging buffer (async on the current stream)."""
+    key = tab.shape
+    buf = _pinned.get(key)
+    if buf is None:
+        buf = _pinned[key] = torch.empty(tab.shape, dtype=torch.float32).pin_memory()
+    buf.numpy()[...] = tab
+    return buf.to(device, non_blocking=True)
+
+
+def slice_imgs(imgs, count, size=224, transform=None, align='uniform', macro=0.):
+    """Drop-in for utils.py:218-254. Returns a list with one [count_local,3,size,size] tensor per input image
+    (count_local == count on one GPU; the contiguous shard of this rank under torchrun)."""
+    _dist.init()
+    kind = _transform_kind(transform)
+    for img in imgs:
+        require_cuda(img, 'slice_imgs input')
+    hw = tuple(imgs[0].shape[2:])
+    assert all(tuple(i.shape[2:]) == hw for i in imgs), 'slice_imgs: all images must share one size'
+    tables, (pad_top, pad_left, fh, fw) = _rng.draw_crop_table(count, hw, size, kind, align, macro, n_imgs=len(imgs))
+    lo, hi = _rng.shard_range(count, _dist.rank(), _dist.world())
+    sliced = []
+    for img, tab in zip(imgs, tables):
+        assert img.shape[0] == 1 and img.shape[1] == 3, 'slice_imgs expects [1,3,H,W] images'
+        local = np.ascontiguousarray(tab[lo:hi])
+        tdev = _table_to_device(local, img.device)
+        meta = (hw[0], hw[1], pad_top, pad_left, hi - lo, size, kind, float(hi - lo) / float(count))
+        sliced.append(_SliceImgs.apply(img, tdev, meta))
+    return sliced
+
+
+def apply_transform_standalone(x, transform):
+    """transform(x) outside slice_imgs: every image of the batch is an identity crop (csize == size)."""
+    require_cuda(x, 'transform input')
+    n, c, h, w = x.shape
+    assert c == 3 and h == w, 'fused transforms expect [N,3,s,s]'
+    outs = []
+    for i in range(n):
+        tab = np.zeros((1, _rng.CROP_PARAM_FLOATS), np.float32)
+        tab[0, _rng.F_CSIZE] = h
+        tab[0, _rng.F_ROT:_rng.F_ROT + 4] = (1., 0., 0., 1.)
+        if transform.kind == _rng.TF_FAST:
+            tab[0, _rng.F_FLAGS] = _rng.draw_fast(tab[0], h)
+        tdev = torch.from_numpy(tab).to(x.device)
+        meta = (h, w, 0, 0, 1, h, transform.kind, 1.)
+        outs.append(_SliceImgs.apply(x[i:i + 1], tdev, meta))
+    return torch.cat(outs, 0)
+
+
+# ---------------------------------------------------------------------------------------------- loss
+class _SimFused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v1, v2, kind):
+        a = v1.detach().contiguous().float().reshape(-1, v1.shape[-1])
+        b = v2.detach().contiguous().float().reshape(-1, v2.shape[-1])
+        S, D = b.shape
+        val = torch.empty((), device=b.device, dtype=torch.float32)
+        g1 = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        g2 = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        check(lib().aph_sim_fwd(a.data_ptr(), a.shape[0], b.data_ptr(), S, D, kind, val.data_ptr(),
+                                g1.data_ptr() if g1 is not None else None, g2.data_ptr() if g2 is not None else None, stream_ptr()),
+              'aph_sim_fwd')
+        ctx.shapes = (v1.shape, v2.shape)
+        ctx.save_for_backward(*[t for t in (g1, g2) if t is not None])
+        ctx.has = (g1 is not None, g2 is not None)
+        return val
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = list(ctx.saved_tensors)
+        g1 = saved.pop(0) if ctx.has[0] else None
+        g2 = saved.pop(0) if ctx.has[1] else None
+        return (g * g1).reshape(ctx.shapes[0]) if g1 is not None else None, (g * g2).reshape(ctx.shapes[1]) if g2 is not None else None, None
+
+
+def dot_compare(v1, v2, cossim_pow=0):
+    dot = (v1 * v2).sum()
+    mag = torch.sqrt(torch.sum(v2 ** 2))
+    cossim = dot / (1e-6 + mag)
+    return dot * cossim ** cossim_pow
+
+
+def sim_func(v1, v2, type=None):
+    """Drop-in for utils.py:276-295. The script's defaults ('mix'; plain cosine with --dualmod) run in one fused
+    kernel; the rarely used 'spher' / 'ang' / 'dot' variants are composed from torch ops on the [S,512] embeddings."""
+    fused_kind = None
+    if type is not None and 'mix' in type:
+        fused_kind = 1
+    elif type is None or not any(k in type for k in ('spher', 'ang', 'dot')):
+        fused_kind = 0
+    if fused_kind is not None and v1.is_cuda and v2.is_cuda and v1.dim() == 2 and v2.dim() == 2 and v1.shape[-1] == v2.shape[-1]:
+        if v1.shape[0] in (1, v2.shape[0]):
+            return _SimFused.apply(v1, v2, fused_kind)
+        if v2.shape[0] == 1:                                 # both similarities are symmetric in their arguments
+            return _SimFused.apply(v2, v1, fused_kind)
+    if type is not None and 'mix' in type:
+        coss = torch.cosine_similarity(v1, v2, dim=-1).mean()
+        a = F.normalize(v1, dim=-1); b = F.normalize(v2, dim=-1)
+        spher = torch.abs((a - b).norm(dim=-1).div(2).arcsin().pow(2).mul(2)).mean()
+        return coss - 0.25 * spher
+    elif type is not None and 'spher' in type:
+        a = F.normalize(v1, dim=-1); b = F.normalize(v2, dim=-1)
+        return (a - b).norm(dim=-1).div(2).arcsin().pow(2).mul(2)
+    elif type is not None and 'ang' in type:
+        return 1 - torch.acos(torch.cosine_similarity(v1, v2, dim=-1)).mean() / np.pi
+    elif type is not None and 'dot' in type:
+        return dot_compare(v1, v2, cossim_pow=1)
+    return torch.cosine_similarity(v1, v2, dim=-1).mean()
+
+
+# ---------------------------------------------------------------------------------------------- helpers clip_fft.py imports
+def old_torch():
+    ver = [int(i) for i in torch.__version__.split('.')[:2]]
+    return True if (ver[0] < 2 and ver[1] < 8) else False
+
+
+def txt_clean(txt):
+    return txt.translate(str.maketrans(dict.fromkeys(list("\n',.вЂ”|!?/:;\\"), ""))).replace(' ', '_').replace('"', '')
+
+
+def basename(file):
+    return os.path.splitext(os.path.basename(file))[0]
+
+
+def img_list(path, subdir=None):
+    if subdir is True:
+        files = [os.path.join(dp, f) for dp, dn, fn in os.walk(path) for f in fn]
+    else:
+        files = [os.path.join(path, f) for f in os.listdir(path)]
+    files = [f for f in files if os.path.splitext(f.lower())[1][1:] in ['jpg', 'jpeg', 'png', 'ppm', 'tif']]
+    return sorted([f for f in files if os.path.isfile(f)])
+
+
+def img_read(path):
+    from imageio import imread
+    img = imread(path)
+    if (img.ndim == 2) or (img.shape[2] == 1):
+        img = np.dstack((img, img, img))
+    if img.shape[2] == 4:
+        img = img[:, :, :3]
+    return img
+
+
+def checkout(img, fname=None, verbose=False):
+    """utils.py:94-100: CHW float -> HWC uint8 -> file (rank 0 only under torchrun). The cv2 preview is dropped."""
+    img = np.transpose(np.array(img)[:, :, :], (1, 2, 0))
+    if fname is not None and _dist.rank() == 0:
+        from imageio import imsave
+        img = np.clip(img * 255, 0, 255).astype(np.uint8)
+        imsave(fname, img)
+
+
+def derivat(img, mode='sobel'):
+    """utils.py:256-268 (the script only ever passes mode='naiv', i.e. the finite-difference branch)."""
+    if mode in ('scharr', 'sobel'):
+        raise NotImplementedError('aphantasia_b200.derivat: only the finite-difference mode used by clip_fft.py is provided')
+    dx = torch.mean(torch.abs(img[:, :, :, 1:] - img[:, :, :, :-1]))
+    dy = torch.mean(torch.abs(img[:, :, 1:, :] - img[:, :, :-1, :]))
+    return 0.5 * (dx + dy)
+
+
+def aesthetic_model(clip_model='vit_b_32'):
+    raise NotImplementedError('aphantasia_b200: --aest downloads a checkpoint (no network here); out of the hot path')
+
+
+def plot_text(txt, size=224):
+    raise NotImplementedError('aphantasia_b200: plot_text needs matplotlib; never called by clip_fft.py')

@@ -1,0 +1,149 @@
+/* aphb200.h -- C ABI of libaphb200.so: the B200-native (sm_100a) hot path of eps696/aphantasia.
+ *
+ * Drop-in boundary. Plain pointers and sizes only; no torch types. Every compute entry
+ * point is asynchronous on the caller's `stream` (pass torch.cuda.current_stream().cuda_stream as void*),
+ * returns 0 on success / non-zero on error (message: aph_last_error(), thread-local), and never owns
+ * user-visible memory: inputs/outputs are caller-owned DEVICE pointers (fp32 unless stated). Scratch lives
+ * in library-owned handles so it survives the reference's per-step torch.cuda.empty_cache()
+ * (/root/reference/clip_fft.py:285).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to /root/reference).
+ * The Python binding (ctypes) is aphantasia_b200/_lib.py; INTEGRATION.md shows the reference-side stub.
+ */
+#ifndef APHB200_H_
+#define APHB200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APH_ABI_VERSION 1
+
+/* ---- crop parameter table: one row per crop, APH_CROP_PARAM_FLOATS float32 values.
+ * Built on the host by replaying the reference's RNG order (aphantasia_b200/_rng.py).               */
+#define APH_CROP_PARAM_FLOATS 24
+#define APH_F_OFFY   0   /* crop top-left y in the sampling frame (integer-valued)   utils.py:247 */
+#define APH_F_OFFX   1   /* crop top-left x                                          utils.py:246 */
+#define APH_F_CSIZE  2   /* crop side in canvas pixels                                utils.py:245 */
+#define APH_F_FLAGS  3   /* bit0 perspective, bit1 erase, bit2 rotate                              */
+#define APH_F_PERSP  4   /* 8 coeffs a..h, output->input (torchvision _get_perspective_coeffs)     */
+#define APH_F_ER_I   12  /* erase rect top, left, height, width (torchvision RandomErasing)        */
+#define APH_F_ER_J   13
+#define APH_F_ER_H   14
+#define APH_F_ER_W   15
+#define APH_F_ROT    16  /* theta00, theta01, theta10, theta11 of the inverse affine matrix        */
+#define APH_F_ANGLE  20  /* degrees, informational                                                 */
+#define APH_FLAG_PERSP 1
+#define APH_FLAG_ERASE 2
+#define APH_FLAG_ROT   4
+
+/* sampler transform kinds (what `transform=` of slice_imgs was)                                  */
+#define APH_TF_NONE      0   /* bicubic resize only                                                */
+#define APH_TF_NORMALIZE 1   /* + transforms.normalize()            transforms.py:102-109          */
+#define APH_TF_FAST      2   /* transforms.transforms_fast          transforms.py:165-170          */
+
+/* similarity kinds (sim_func `type`)                                         utils.py:276-295    */
+#define APH_SIM_COS 0
+#define APH_SIM_MIX 1
+
+int         aph_version(void);
+const char* aph_last_error(void);
+
+/* ================= L3: spectrum -> RGB synthesis =============================================
+ * Replaces fft_image.inner (aphantasia/image.py:164-175) and, fused, to_valid_rgb.inner
+ * (aphantasia/image.py:21-28):   x = irfftn(scale*(P [+shift]), s=(H,W), 'ortho');
+ *                                 img = x*contrast/std(x);  out = sigmoid(colmat . img)            */
+typedef struct aph_fft_plan aph_fft_plan;
+int aph_fft_plan_create(aph_fft_plan** plan, int H, int W);   /* H, W: prime factors <= 13 */
+int aph_fft_plan_destroy(aph_fft_plan* plan);
+
+/* params [3,H,Wh,2], scale [H,Wh] (Wh = W/2+1).  shift_mode 0: none; 1: shift [H,Wh] (the script's
+ * --noise, clip_fft.py:238); 2: shift [3,H,Wh,2] (illustra.py:334).
+ * colmat: 9 floats, HOST pointer, row-major Mn[d][c] (out_d = sum_c Mn[d][c] img_c) or NULL = no
+ * decorrelation. apply_sigmoid 0/1.
+ * Outputs: x_raw [3,H,W] (un-normalised irfft, saved for backward), stats double[4] on device
+ * {sum x, sum x^2, sum g.x (bwd scratch), unused}, out [3,H,W].                                    */
+int aph_synth_fft_fwd(aph_fft_plan* plan, const float* params, const float* scale,
+                      const float* shift, int shift_mode, float contrast,
+                      const float* colmat_host, int apply_sigmoid,
+                      float* x_raw, double* stats, float* out, void* stream);
+/* grad_out [3,H,W] = dL/d out  ->  grad_params [3,H,Wh,2] (overwritten).                           */
+int aph_synth_fft_bwd(aph_fft_plan* plan, const float* grad_out, const float* out,
+                      const float* x_raw, double* stats, const float* scale, float contrast,
+                      const float* colmat_host, int apply_sigmoid,
+                      float* grad_params, void* stream);
+
+/* Stand-alone to_valid_rgb for a foreign image_f (aphantasia/image.py:21-28): img [3,H,W] -> out.  */
+int aph_valid_rgb_fwd(const float* img, int64_t hw, const float* colmat_host, float* out, void* stream);
+int aph_valid_rgb_bwd(const float* grad_out, const float* out, int64_t hw, const float* colmat_host,
+                      float* grad_img, void* stream);
+
+/* ================= L2: multi-crop sampler =====================================================
+ * Replaces the per-crop Python loop of slice_imgs (aphantasia/utils.py:243-253) + transforms_fast
+ * (aphantasia/transforms.py:165-170): bicubic(A=-0.75, align_corners, crop-clamped) -> perspective
+ * (bilinear, zeros, x coverage) -> erase -> rotate (bilinear, zeros, x coverage) -> normalise.
+ * canvas [3,H,W]; the sampling frame is the canvas wrap-padded by (pad_top, pad_left)
+ * ('over*' aligns, utils.py:152-187; 0,0 otherwise); table: DEVICE [S, APH_CROP_PARAM_FLOATS];
+ * out [S,3,size,size]. size*size*4 bytes must fit one CTA's shared memory (size <= 238).           */
+int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, int pad_left,
+                   const float* table, int S, int size, int kind, float* out, void* stream);
+/* grad_out [S,3,size,size] -> grad_canvas [3,H,W] (zeroed here, then accumulated).                 */
+int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, int pad_left,
+                   const float* table, int S, int size, int kind, float* grad_canvas, void* stream);
+
+/* ================= L1: CLIP ViT-B image encoder ===============================================
+ * Replaces clip.model.CLIP.encode_image / VisionTransformer.forward (third-party OpenAI clip; call
+ * sites clip_fft.py:216,254,276) and its autograd data-gradient. Weights are frozen: no weight
+ * gradients are computed (the reference computes and discards them, clip_fft.py:293-295).           */
+typedef struct aph_vit aph_vit;
+typedef struct {
+  int32_t patch;      /* 32 or 16                                   */
+  int32_t width;      /* 768                                        */
+  int32_t layers;     /* 12                                         */
+  int32_t heads;      /* 12 (head dim must be 64)                   */
+  int32_t out_dim;    /* 512                                        */
+  int32_t res;        /* input resolution, 224                      */
+  int32_t max_batch;  /* largest S a call will pass                 */
+  int32_t reserved;
+} aph_vit_config;
+int aph_vit_create(aph_vit** vit, const aph_vit_config* cfg);
+int aph_vit_destroy(aph_vit* vit);
+/* One tensor of the OpenAI state dict, by its key ("visual.conv1.weight", "visual.transformer.
+ * resblocks.3.attn.in_proj_weight", ...), fp32 DEVICE pointer; converted/transposed to the packed
+ * bf16 operand layout on device. aph_vit_finalize checks every tensor arrived.                     */
+int aph_vit_load_tensor(aph_vit* vit, const char* key, const float* data, int64_t numel, void* stream);
+int aph_vit_finalize(aph_vit* vit);
+/* images [S,3,res,res] fp32 (already normalised) -> emb [S,out_dim] fp32. save_for_bwd 0/1.        */
+int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb, int save_for_bwd, void* stream);
+/* grad_emb [S,out_dim] -> grad_images [S,3,res,res] (overwritten). Uses activations of the last
+ * aph_vit_fwd(save_for_bwd=1) with the same S.                                                     */
+int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* grad_images, void* stream);
+/* bytes of device memory owned by the handle (weights + activation arena)                          */
+int64_t aph_vit_bytes(const aph_vit* vit);
+
+/* Stand-alone tcgen05 GEMM used by the encoder (exported for tests / profiling):
+ * C[M,N] (fp32) = A[M,K] (bf16, row-major) . B[N,K]^T (bf16, row-major). K % 64 == 0, N % 128 == 0. */
+int aph_gemm_bf16_tn(const void* A, const void* B, float* C, int M, int N, int K, void* stream);
+
+/* ================= L1: similarity loss ========================================================
+ * Replaces sim_func(v1, v2, type) for type in {None/'cossim', 'mix'} (aphantasia/utils.py:276-282,
+ * 295). v1 [n1,D] with n1 in {1,S}; v2 [S,D]. value (device scalar) = mean_s f(v1, v2_s).
+ * grad_v1 / grad_v2 may be NULL; they receive d value / d v (not yet multiplied by the upstream
+ * gradient).                                                                                       */
+int aph_sim_fwd(const float* v1, int n1, const float* v2, int S, int D, int kind,
+                float* value, float* grad_v1, float* grad_v2, void* stream);
+
+/* ================= step glue ==================================================================
+ * torch.optim.Adam(betas=(b1,b2)) single-tensor update (clip_fft.py:108-115,295), bias-corrected. */
+int aph_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
+                  float lr, float b1, float b2, float eps, int step, void* stream);
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches)                 */
+int64_t aph_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APHB200_H_ */

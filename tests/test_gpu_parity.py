@@ -1,0 +1,240 @@
+"""GPU parity tests: every CUDA kernel of libaphb200.so, called through the C ABI (ctypes) / the drop-in entry
+points, against the CPU oracle (oracle/restate.py) and the committed reference fixtures, on identical seeds.
+
+Tolerances (norm-wise relative error, BASELINE.json north_star): 1e-3 for the fp32 kernels (we hold them to
+much tighter bounds below), 2e-2 for the bf16 tensor-core path of the ViT.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import restate as R  # noqa: E402
+
+
+def _rel(a, b):
+    a = torch.as_tensor(np.asarray(a.detach().cpu() if torch.is_tensor(a) else a)).double()
+    b = torch.as_tensor(np.asarray(b.detach().cpu() if torch.is_tensor(b) else b)).double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _seed(s):
+    torch.manual_seed(int(s)); np.random.seed(int(s))
+
+
+@pytest.fixture(scope='module')
+def L():
+    from aphantasia_b200 import _lib
+    assert torch.cuda.is_available()
+    return _lib
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 256, 128), (300, 384, 192), (1000, 768, 3072), (9500, 2304, 768), (190, 512, 768)])
+def test_tcgen05_gemm(L, M, N, K):
+    _seed(M + N + K)
+    a = torch.randn(M, K, device='cuda').bfloat16()
+    b = torch.randn(N, K, device='cuda').bfloat16()
+    c = torch.full((M, N), float('nan'), device='cuda')
+    L.check(L.lib().aph_gemm_bf16_tn(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, L.stream_ptr()), 'gemm')
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().T
+    assert torch.isfinite(c).all()
+    assert _rel(c, ref) < 1e-5          # bf16 products are exact in fp32; only the accumulation order differs
+
+
+# ---------------------------------------------------------------------------------------------- synth
+def _run_synth(L, params, h, w, decay, colors, contrast, shift=None, cot=None):
+    from aphantasia_b200.image import FFTImage, to_valid_rgb
+    p = torch.tensor(params).cuda().requires_grad_(True)
+    gen = FFTImage(p, h, w, decay)
+    rgb_f = to_valid_rgb(gen, colors=colors)
+    img = gen(None, contrast)
+    rgb = rgb_f(shift, contrast) if shift is not None else rgb_f(contrast=contrast)
+    grad = None
+    if cot is not None:
+        (rgb * torch.tensor(cot).cuda()).sum().backward()
+        grad = p.grad
+    return img, rgb, grad
+
+
+@pytest.mark.parametrize('name', ['even', 'odd', 'sq'])
+def test_synth_fft_vs_reference_golden(L, golden, name):
+    h, w, decay, colors, contrast = (float(v) for v in golden['fft_%s_cfg' % name])
+    h, w = int(h), int(w)
+    img, rgb, grad = _run_synth(L, golden['fft_%s_params' % name], h, w, decay, colors, contrast, cot=golden['fft_%s_cot' % name])
+    assert _rel(img, golden['fft_%s_img' % name]) < 2e-5
+    assert _rel(rgb, golden['fft_%s_rgb' % name]) < 2e-5
+    assert _rel(grad, golden['fft_%s_grad' % name]) < 1e-4
+    _, rgb_s, _ = _run_synth(L, golden['fft_%s_params' % name], h, w, decay, colors, contrast, shift=torch.tensor(golden['fft_%s_shift' % name]))
+    assert _rel(rgb_s, golden['fft_%s_rgb_shift' % name]) < 2e-5
+
+
+@pytest.mark.parametrize('h,w', [(224, 224), (720, 1280), (135, 90), (1080, 1920)])
+def test_synth_fft_vs_oracle(L, h, w):
+    _seed(h * 7 + w)
+    params = 0.01 * torch.randn(1, 3, h, w // 2 + 1, 2)
+    cot = torch.randn(1, 3, h, w)
+    img, rgb, grad = _run_synth(L, params.numpy(), h, w, 1.5, 1.8, 1.0, cot=cot.numpy())
+    p = params.clone().requires_grad_(True)
+    scale = R.fft_scale(h, w, 1.5)
+    o_img = R.synth_fft(p, scale, h, w)
+    o_rgb = R.valid_rgb(o_img, R.color_matrix(1.8))
+    (o_rgb * cot).sum().backward()
+    assert _rel(img, o_img) < 5e-5
+    assert _rel(rgb, o_rgb) < 5e-5
+    assert _rel(grad, p.grad) < 2e-4
+
+
+def test_valid_rgb_standalone(L):
+    from aphantasia_b200.image import to_valid_rgb
+    _seed(3)
+    x = torch.randn(1, 3, 40, 56)
+    cot = torch.randn(1, 3, 40, 56)
+    xc = x.cuda().requires_grad_(True)
+    out = to_valid_rgb(lambda: xc, colors=1.8)()
+    (out * cot.cuda()).sum().backward()
+    xo = x.clone().requires_grad_(True)
+    ref = R.valid_rgb(xo, R.color_matrix(1.8))
+    (ref * cot).sum().backward()
+    assert _rel(out, ref) < 1e-6 and _rel(xc.grad, xo.grad) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- sampler
+@pytest.mark.parametrize('name', ['small', 'mid', 'over'])
+def test_sampler_vs_reference_golden(L, golden, name):
+    from aphantasia_b200 import transforms
+    from aphantasia_b200.utils import slice_imgs
+    H, W, cnt, size, macro, s, sub = (float(v) for v in golden['smp_%s_cfg' % name])
+    H, W, cnt, size, s, sub = int(H), int(W), int(cnt), int(size), int(s), int(sub)
+    align = str(golden['smp_%s_align' % name])
+    canvas = torch.tensor(golden['smp_%s_canvas' % name].astype(np.float32)).cuda().requires_grad_(True)
+    _seed(s)
+    out = slice_imgs([canvas], cnt, size, transforms.transforms_fast, align, macro)[0]
+    assert _rel(out[:, :, ::sub, ::sub], golden['smp_%s_out' % name]) < 1e-5
+    _seed(int(golden['smp_%s_cot_seed' % name]))
+    cot = torch.randn(out.shape)
+    (out * cot.cuda()).sum().backward()
+    st = max(1, sub // 2)
+    assert _rel(canvas.grad[:, :, ::st, ::st], golden['smp_%s_gcanvas' % name]) < 1e-4
+
+
+@pytest.mark.parametrize('kind', [0, 1, 2])
+def test_sampler_vs_oracle_720p(L, kind):
+    from aphantasia_b200 import _rng, transforms
+    from aphantasia_b200.utils import slice_imgs
+    tf = [None, transforms.normalize(), transforms.transforms_fast][kind]
+    _seed(11)
+    canvas = torch.rand(1, 3, 360, 640)
+    S = 24
+    cc = canvas.cuda().requires_grad_(True)
+    _seed(5)
+    out = slice_imgs([cc], S, 224, tf, 'uniform', 0.4)[0]
+    _seed(5)
+    tabs, frame = _rng.draw_crop_table(S, (360, 640), 224, kind, 'uniform', 0.4)
+    co = canvas.clone().requires_grad_(True)
+    ref = R.sample_crops(co, tabs[0], 224, kind)
+    _seed(6)
+    cot = torch.randn(ref.shape)
+    (out * cot.cuda()).sum().backward()
+    (ref * cot).sum().backward()
+    assert _rel(out, ref) < 1e-5
+    assert _rel(cc.grad, co.grad) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- loss / adam
+@pytest.mark.parametrize('t', [None, 'mix', 'cossim'])
+def test_sim_func_vs_reference_golden(L, golden, t):
+    from aphantasia_b200.utils import sim_func
+    v1 = torch.tensor(golden['sim_v1']).cuda(); v2 = torch.tensor(golden['sim_v2']).cuda().requires_grad_(True)
+    val = sim_func(v1, v2, t)
+    val.backward()
+    assert _rel(val, golden['sim_%s_val' % t]) < 1e-5
+    assert _rel(v2.grad, golden['sim_%s_grad' % t]) < 1e-4
+
+
+def test_sim_func_pairwise_and_other_kinds(L, golden):
+    from aphantasia_b200.utils import sim_func
+    _seed(8)
+    a = torch.randn(9, 512); b = torch.randn(9, 512)
+    ac = a.cuda().requires_grad_(True); bc = b.cuda().requires_grad_(True)
+    ao = a.clone().requires_grad_(True); bo = b.clone().requires_grad_(True)
+    sim_func(ac, bc, 'mix').backward(); R.sim_func(ao, bo, 'mix').backward()
+    assert _rel(ac.grad, ao.grad) < 1e-4 and _rel(bc.grad, bo.grad) < 1e-4
+    v1 = torch.tensor(golden['sim_v1']).cuda(); v2 = torch.tensor(golden['sim_v2']).cuda()
+    for t in ('ang', 'dot'):
+        assert _rel(sim_func(v1, v2, t), golden['sim_%s_val' % t]) < 1e-5
+
+
+def test_adam_step(L):
+    _seed(2)
+    p0 = torch.randn(5000); g = [torch.randn(5000) for _ in range(3)]
+    p = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p], 0.05, betas=(.0, .999))
+    pc = p0.cuda(); m = torch.zeros_like(pc); v = torch.zeros_like(pc)
+    for i, gi in enumerate(g):
+        p.grad = gi.clone(); opt.step()
+        gc = gi.cuda()
+        L.check(L.lib().aph_adam_step(pc.data_ptr(), gc.data_ptr(), m.data_ptr(), v.data_ptr(), pc.numel(), 0.05, 0.0, 0.999, 1e-8, i + 1,
+                                      L.stream_ptr()), 'adam')
+    assert _rel(pc, p) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- ViT
+def _vit_pair(patch, width, layers, heads, out, res, seed):
+    from aphantasia_b200.clip import VisionTransformer
+    sd = R.synthetic_visual_state_dict(patch, seed, width, layers, heads, out, res)
+    return VisionTransformer(sd), R.build_visual(sd)
+
+
+@pytest.mark.parametrize('cfg', [dict(patch=16, width=128, layers=2, heads=2, out=128, res=64, S=5),
+                                 dict(patch=32, width=256, layers=3, heads=4, out=128, res=224, S=7),
+                                 dict(patch=32, width=768, layers=12, heads=12, out=512, res=224, S=3),
+                                 dict(patch=16, width=768, layers=12, heads=12, out=512, res=224, S=2)])
+def test_vit_forward_backward_vs_oracle(L, cfg):
+    S, res = cfg['S'], cfg['res']
+    ours, ref = _vit_pair(cfg['patch'], cfg['width'], cfg['layers'], cfg['heads'], cfg['out'], res, 0)
+    _seed(4)
+    x = torch.randn(S, 3, res, res)
+    cot = torch.randn(S, cfg['out'])
+    xc = x.cuda().requires_grad_(True)
+    emb = ours(xc)
+    (emb * cot.cuda()).sum().backward()
+    xo = x.clone().requires_grad_(True)
+    eo = ref(xo)
+    (eo * cot).sum().backward()
+    e_emb, e_grad = _rel(emb, eo), _rel(xc.grad, xo.grad)
+    print('vit %s: rel err emb %.3e grad %.3e' % (cfg, e_emb, e_grad))
+    assert e_emb < 2e-2 and e_grad < 2e-2       # bf16 operands, fp32 accumulation (north_star bf16 tolerance)
+
+
+# ---------------------------------------------------------------------------------------------- whole step (config 1 shape)
+def test_full_step_config1_vs_oracle(L):
+    """BASELINE config 1 shape (224x224 canvas, S=3, ViT-B/32): loss and d loss / d spectrum vs the CPU oracle."""
+    from aphantasia_b200 import _rng, transforms
+    from aphantasia_b200.clip import CLIP, synthetic_visual_state_dict
+    from aphantasia_b200.image import fft_image, to_valid_rgb
+    from aphantasia_b200.utils import sim_func, slice_imgs
+    h = w = 224; S = 3
+    sd = synthetic_visual_state_dict(patch=32, seed=0)
+    model = CLIP('ViT-B/32', sd, True)
+    _seed(0)
+    params, image_f, _ = fft_image([1, 3, h, w], 0.07, 1.5, None)
+    rgb_f = to_valid_rgb(image_f, colors=1.8)
+    txt = model.encode_text(torch.zeros(1, 77, dtype=torch.long)).cuda()
+    _seed(1)
+    crops = slice_imgs([rgb_f()], S, 224, transforms.transforms_fast, 'uniform', 0.4)[0]
+    emb = model.encode_image(crops)
+    loss = -1. * sim_func(txt, emb, 'mix')
+    loss.backward()
+    _seed(1)
+    tabs, _ = _rng.draw_crop_table(S, (h, w), 224, 2, 'uniform', 0.4)
+    o_loss, o_grad, o_emb = R.reference_step(params[0].detach().cpu(), R.fft_scale(h, w, 1.5), (h, w), R.color_matrix(1.8), tabs[0],
+                                             R.build_visual(sd), txt.cpu(), 'mix')
+    print('config1: loss ours %.6f oracle %.6f; rel emb %.3e grad %.3e' % (loss.item(), o_loss.item(), _rel(emb, o_emb), _rel(params[0].grad, o_grad)))
+    assert _rel(emb, o_emb) < 2e-2
+    assert abs(loss.item() - o_loss.item()) < 2e-3
+    assert _rel(params[0].grad, o_grad) < 3e-2
