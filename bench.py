@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- optimisation steps/sec of the Aphantasia hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): clip_fft.py --size 1280-720 --samples 200 ViT-B/32 FFT -> S = int(200*0.95) = 190
+crops (clip_fft.py:167-169), transforms_fast, macro 0.4, 'mix' loss, Adam(lr .05, betas (0,.999)). One "step" = one
+train(i) body without the preview branch (clip_fft.py:235-295): synth fwd -> sample fwd -> ViT fwd -> loss -> ViT
+data-gradient -> sample bwd -> [all-reduce] -> synth bwd -> Adam.
+
+  value : steps/s with everything resident in HBM (crop tables pre-staged), C-ABI calls only, CUDA-event timed.
+  e2e   : steps/s through the reference-facing Python entry points (fft_image / to_valid_rgb / slice_imgs /
+          model.encode_image / sim_func + loss.backward() + torch.optim.Adam), including per step the host RNG replay,
+          the pinned H2D copy of the crop table and a D2H read of the loss.
+  --impl reference : the CPU oracle port of the reference path (oracle/restate.py) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, SAMPLES_FLAG, MODEL, PATCH = 720, 1280, 200, 'ViT-B/32', 32
+S_TOTAL = int(SAMPLES_FLAG * 0.95)
+F_VIT = {32: 8.8176e9, 16: 35.1269e9}      # forward FLOPs per image
+
+
+def vit_gemm_shapes(S, patch=32, D=768, layers=12, out=512, res=224):
+    """(M, N, K) of every tcgen05 GEMM launch of one step (forward + data-gradient)."""
+    g = res // patch; T = g * g + 1; M = S * T; Mp = S * g * g; Kp = 3 * patch * patch
+    fwd = [(Mp, D, Kp)] + layers * [(M, 3 * D, D), (M, D, D), (M, 4 * D, D), (M, D, 4 * D)] + [(S, out, D)]
+    bwd = [(S, D, out)] + layers * [(M, 4 * D, D), (M, D, 4 * D), (M, D, D), (M, D, 3 * D)] + [(Mp, Kp, D)]
+    return fwd + bwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in rows)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(rows[0][1]), 'power_w_max': max(float(r[2]) for r in rows),
+                'samples': len(rows), 'reasons': reasons}
+
+
+# =============================================================================================== ours
+class DeviceStep:
+    """The whole step as direct C-ABI calls on resident buffers (no autograd, no per-step host work but launches)."""
+
+    def __init__(self, S_local, S_total, rank, world, n_tables, seed=0):
+        from aphantasia_b200 import _lib, _rng
+        from aphantasia_b200.clip import VisionTransformer, synthetic_visual_state_dict
+        from aphantasia_b200.image import FFTImage, _color_matrix_host
+        self.L, self.lib = _lib, _lib.lib()
+        self.S, self.S_total, self.world = S_local, S_total, world
+        dev = torch.device('cuda')
+        torch.manual_seed(seed); np.random.seed(seed)
+        self.params = (0.01 * torch.randn(1, 3, H, W // 2 + 1, 2)).to(dev)
+        self.gen = FFTImage(self.params, H, W, 1.5)
+        self.colmat = _color_matrix_host(1.8)
+        self.vis = VisionTransformer(synthetic_visual_state_dict(patch=PATCH, seed=0), max_batch=S_local)
+        g = torch.Generator().manual_seed(1234)
+        txt = torch.randn(1, 512, generator=g); self.txt = (10. * txt / txt.norm()).to(dev)
+        lo, hi = _rng.shard_range(S_total, rank, world)
+        assert hi - lo == S_local
+        tabs = []
+        for _ in range(n_tables):       # every rank replays the full stream, keeps its shard (results independent of N)
+            t, _f = _rng.draw_crop_table(S_total, (H, W), 224, _rng.TF_FAST, 'uniform', 0.4)
+            tabs.append(torch.from_numpy(np.ascontiguousarray(t[0][lo:hi])))
+        self.tables = torch.stack(tabs).to(dev)
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.x_raw = torch.empty(3, H, W, **f32); self.rgb = torch.empty(3, H, W, **f32)
+        self.stats = torch.zeros(4, device=dev, dtype=torch.float64)
+        self.crops = torch.empty(S_local, 3, 224, 224, **f32); self.g_crops = torch.empty_like(self.crops)
+        self.emb = torch.empty(S_local, 512, **f32); self.g_emb = torch.empty_like(self.emb)
+        self.loss = torch.zeros((), **f32)
+        self.g_rgb = torch.empty(3, H, W, **f32); self.g_params = torch.empty_like(self.params)
+        self.m = torch.zeros_like(self.params); self.v = torch.zeros_like(self.params)
+        self.t = 0
+        self.ev = None
+
+    def _mark(self, name):
+        if self.ev is not None:
+            e = torch.cuda.Event(enable_timing=True); e.record(); self.ev.append((name, e))
+
+    def step(self, i):
+        lib, ck, st = self.lib, self.L.check, self.L.stream_ptr()
+        tab = self.tables[i % self.tables.shape[0]]
+        self._mark('start')
+        ck(lib.aph_synth_fft_fwd(self.gen.plan, self.params.data_ptr(), self.gen.scale.data_ptr(), None, 0, 1.0, self.colmat, 1,
+                                 self.x_raw.data_ptr(), self.stats.data_ptr(), self.rgb.data_ptr(), st), 'synth_fwd')
+        self._mark('synth_fwd')
+        ck(lib.aph_sample_fwd(self.rgb.data_ptr(), H, W, 0, 0, tab.data_ptr(), self.S, 224, 2, self.crops.data_ptr(), st), 'sample_fwd')
+        self._mark('sample_fwd')
+        ck(lib.aph_vit_fwd(self.vis.handle, self.crops.data_ptr(), self.S, self.emb.data_ptr(), 1, st), 'vit_fwd')
+        self._mark('vit_fwd')
+        ck(lib.aph_sim_fwd(self.txt.data_ptr(), 1, self.emb.data_ptr(), self.S, 512, 1, self.loss.data_ptr(), None, self.g_emb.data_ptr(), st), 'sim')
+        self.g_emb.mul_(-1.0)                       # loss = -1 * wt * sim (clip_fft.py:116,259)
+        self._mark('loss')
+        ck(lib.aph_vit_bwd(self.vis.handle, self.g_emb.data_ptr(), self.S, self.g_crops.data_ptr(), st), 'vit_bwd')
+        self._mark('vit_bwd')
+        ck(lib.aph_sample_bwd(self.g_crops.data_ptr(), H, W, 0, 0, tab.data_ptr(), self.S, 224, 2, self.g_rgb.data_ptr(), st), 'sample_bwd')
+        self._mark('sample_bwd')
+        if self.world > 1:
+            self.g_rgb.mul_(float(self.S) / float(self.S_total))
+            torch.distributed.all_reduce(self.g_rgb)
+            self._mark('allreduce')
+        ck(lib.aph_synth_fft_bwd(self.gen.plan, self.g_rgb.data_ptr(), self.rgb.data_ptr(), self.x_raw.data_ptr(), self.stats.data_ptr(),
+                                 self.gen.scale.data_ptr(), 1.0, self.colmat, 1, self.g_params.data_ptr(), st), 'synth_bwd')
+        self._mark('synth_bwd')
+        self.t += 1
+        ck(lib.aph_adam_step(self.params.data_ptr(), self.g_params.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.params.numel(),
+                             0.05, 0.0, 0.999, 1e-8, self.t, st), 'adam')
+        self._mark('adam')
+
+
+class ApiStep:
+    """The same step through the reference-facing Python entry points (what clip_fft.py's train(i) executes)."""
+
+    def __init__(self, seed=0):
+        from aphantasia_b200 import transforms
+        from aphantasia_b200.clip import CLIP, synthetic_visual_state_dict
+        from aphantasia_b200.image import fft_image, to_valid_rgb
+        from aphantasia_b200.utils import sim_func, slice_imgs
+        self.slice_imgs, self.sim_func, self.tf = slice_imgs, sim_func, transforms.transforms_fast
+        torch.manual_seed(seed); np.random.seed(seed)
+        self.params, image_f, _ = fft_image([1, 3, H, W], 0.07, 1.5, None)
+        self.image_f = to_valid_rgb(image_f, colors=1.8)
+        self.model = CLIP(MODEL, synthetic_visual_state_dict(patch=PATCH, seed=0), True)
+        g = torch.Generator().manual_seed(1234)
+        txt = torch.randn(1, 512, generator=g); self.txt = (10. * txt / txt.norm()).cuda()
+        self.opt = torch.optim.Adam(self.params, 0.05, betas=(.0, .999))
+
+    def step(self, i):
+        img_out = self.image_f(None)
+        img_sliced = self.slice_imgs([img_out], S_TOTAL, 224, self.tf, 'uniform', 0.4)[0]
+        out_enc = self.model.encode_image(img_sliced)
+        loss = -1. * 1. * self.sim_func(self.txt, out_enc, 'mix')
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return loss.item()                          # D2H read of the step's result
+
+
+def timed(fn, steps, warmup, dist_barrier):
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize(); dist_barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize(); dist_barrier()
+    return e0.elapsed_time(e1) / 1e3
+
+
+def cpu_baseline_port(sample_S, threads=None):
+    """Times the oracle port of the reference step on the host cores on a bounded sample (sample_S of the 190 crops,
+    full 1280x720 canvas) and extrapolates linearly in the crop count; synth fwd/bwd is measured at full size."""
+    from aphantasia_b200 import _rng
+    from aphantasia_b200.clip import synthetic_visual_state_dict
+    from oracle import restate as R
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0); np.random.seed(0)
+    params = 0.01 * torch.randn(1, 3, H, W // 2 + 1, 2)
+    scale, cm = R.fft_scale(H, W, 1.5), R.color_matrix(1.8)
+    vis = R.build_visual(synthetic_visual_state_dict(patch=PATCH, seed=0))
+    g = torch.Generator().manual_seed(1234)
+    txt = torch.randn(1, 512, generator=g); txt = 10. * txt / txt.norm()
+    tabs, _ = _rng.draw_crop_table(S_TOTAL, (H, W), 224, _rng.TF_FAST, 'uniform', 0.4)
+
+    def step(S):
+        t0 = time.perf_counter()
+        R.reference_step(params, scale, (H, W), cm, tabs[0][:S], vis, txt, 'mix')
+        return time.perf_counter() - t0
+    step(1)                                          # warm-up (allocator, thread pool)
+    t1 = step(1)
+    tS = step(sample_S)
+    per_crop = max(tS - t1, 1e-9) / max(sample_S - 1, 1)
+    t_full = t1 + per_crop * (S_TOTAL - 1)
+    return {'value': 1.0 / t_full, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
+            'sample': 'oracle/restate.py reference_step (fp32, incl. the CLIP weight-gradients the reference also computes), 1280x720 canvas, '
+                      '%d of %d crops timed (%.2fs) + 1-crop step (%.2fs), extrapolated linearly in crops to %.2fs/step' % (sample_S, S_TOTAL, tS, t1, t_full)}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl')
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    from aphantasia_b200 import _lib, _rng
+    lo, hi = _rng.shard_range(S_TOTAL, rank, world)
+    K, Wm = args.steps, args.warmup
+
+    # ---- device-resident leg (value)
+    ds = DeviceStep(hi - lo, S_TOTAL, rank, world, n_tables=min(K + Wm, 32))
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.lib().aph_launch_count()
+    t_dev = timed(ds.step, K, Wm, barrier)
+    launches = (_lib.lib().aph_launch_count() - l0) * K // (K + Wm)
+    clk = clocks.stop() if clocks else None
+    # per-stage split + GEMM-kernel timing, measured live right after the timed region (same process, same buffers)
+    ds.ev = []
+    for i in range(3):
+        ds.step(i)
+    torch.cuda.synchronize()
+    stages = {}
+    for (n0, e0), (n1, e1) in zip(ds.ev[:-1], ds.ev[1:]):
+        if n1 != 'start':
+            stages[n1] = stages.get(n1, 0.) + e0.elapsed_time(e1) / 3
+    ds.ev = None
+    gemm = time_gemms(ds, hi - lo) if os.environ.get('APH_BENCH_GEMM', '1') == '1' else {'ms': 0., 'tflops': 0., 'launches': 0}
+    t = torch.tensor([t_dev], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_dev = float(t.item())
+    del ds
+    torch.cuda.empty_cache()
+
+    if os.environ.get('APH_BENCH_LEGS', 'all') == 'device':      # profiling runs (ncu) only need the resident leg
+        if rank == 0:
+            print(json.dumps({'value': K / t_dev, 'ms_per_step': 1e3 * t_dev / K, 'stages_ms': stages, 'gemm': gemm, 'note': 'device leg only'}))
+        return
+    # ---- end-to-end leg through the public API (e2e)
+    from aphantasia_b200 import _dist
+    os.environ['APH_SYNC_SEED'] = '0'
+    _dist.init()
+    api = ApiStep()
+    t_api = timed(api.step, K, Wm, barrier)
+    t = torch.tensor([t_api], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_api = float(t.item())
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
+    flops_vit = 2.0 * (hi - lo) * F_VIT[PATCH]
+    out = {
+        'metric': 'optimization steps/sec @1280x720 FFT, 200 samples, ViT-B/32', 'value': K / t_dev, 'unit': 'steps/s',
+        'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': 1e3 * t_dev / K, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic (seeded spectrum, seeded synthetic ViT-B/32 weights, seeded text embedding)',
+        'config': {'workload': 'clip_fft.py --size 1280-720 --samples 200 ViT-B/32 FFT: S=190 crops/step, transforms_fast, mix loss, Adam',
+                   'parallelism': 'samples sharded over %d GPU(s), one NCCL all-reduce of dRGB per step' % world if world > 1 else 'single GPU',
+                   'l2': 'working set per step (~1.9 GB of saved activations) exceeds the 126 MB L2; no explicit flush'},
+        'e2e': {'value': K / t_api, 'unit': 'steps/s', 'h2d_bytes_per_step': (hi - lo) * 24 * 4, 'd2h_bytes_per_step': 4,
+                'ms_per_step': 1e3 * t_api / K, 'path': 'fft_image/to_valid_rgb/slice_imgs/encode_image/sim_func + backward + torch.optim.Adam'},
+        'gpu_launches': int(launches),
+        'clocks': clk,
+        'roofline': {'bound': 'tensor', 'kernel': 'k_gemm_bf16_tn (tcgen05, all %d launches of one step)' % gemm['launches'],
+                     'achieved': gemm['tflops'], 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': gemm['tflops'] / peak_tf, 'traffic': None,
+                     'peak_source': peak_src, 'gemm_ms_per_step': gemm['ms'],
+                     'vit_step_frac': (flops_vit / (1e-3 * (stages.get('vit_fwd', 0) + stages.get('vit_bwd', 0)) + 1e-12)) / 1e12 / peak_tf},
+        'stages_ms': {k: round(v, 4) for k, v in stages.items()},
+    }
+    if world == 1:
+        try:
+            out['cpu_baseline'] = cpu_baseline_port(sample_S=4)
+        except Exception as ex:      # the baseline must never take the bench line down
+            out['cpu_baseline'] = {'value': None, 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': 'failed: %r' % (ex,)}
+    print(json.dumps(out))
+
+
+def time_gemms(ds, S):
+    """Average duration of the step's tcgen05 GEMM launches: each shape of the step replayed on the handle's own
+    operand-sized buffers with CUDA events on the launching stream (after warm-up)."""
+    from aphantasia_b200 import _lib
+    lib, ck = _lib.lib(), _lib.check
+    shapes = vit_gemm_shapes(S, PATCH)
+    uniq = sorted(set(shapes))
+    st = _lib.stream_ptr()
+    per = {}
+    for (M, N, K) in uniq:
+        a = torch.randn(M, K, device='cuda').bfloat16(); b = torch.randn(N, K, device='cuda').bfloat16()
+        c = torch.empty(M, N, device='cuda')
+        for _ in range(3):
+            ck(lib.aph_gemm_bf16_tn(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, st), 'gemm')
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ck(lib.aph_gemm_bf16_tn(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, st), 'gemm')
+        e1.record(); torch.cuda.synchronize()
+        per[(M, N, K)] = e0.elapsed_time(e1) / reps
+    ms = sum(per[s] for s in shapes)
+    fl = sum(2.0 * m * n * k for (m, n, k) in shapes)
+    return {'ms': ms, 'tflops': fl / (ms * 1e-3) / 1e12, 'launches': len(shapes),
+            'per_shape_ms': {'%dx%dx%d' % s: round(v, 4) for s, v in per.items()}}
+
+
+# =============================================================================================== reference arm
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    K, Wm = max(args.steps, 1), args.warmup
+    # bounded sample per step so that the whole run ends within a few minutes
+    budget = 150.0
+    probe = cpu_baseline_port(sample_S=2)
+    t_full = 1.0 / probe['value']
+    per_crop = t_full / S_TOTAL
+    sample_S = int(max(2, min(S_TOTAL, budget / max(K + Wm, 1) / max(per_crop, 1e-6))))
+    vals = []
+    for i in range(Wm + K):
+        r = cpu_baseline_port(sample_S=sample_S)
+        if i >= Wm:
+            vals.append(r['value'])
+    v = float(np.median(vals))
+    r['value'] = v
+    out = {'impl': 'reference', 'metric': 'optimization steps/sec @1280x720 FFT, 200 samples, ViT-B/32', 'value': v, 'unit': 'steps/s',
+           'n_gpus': args.gpus, 'steps': K, 'warmup': Wm, 'ms_per_step': 1e3 / v, 'higher_is_better': True, 'scaling': 'strong',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (same seeds / shapes as the GPU arm)',
+           'config': {'workload': 'clip_fft.py --size 1280-720 --samples 200 ViT-B/32 FFT: S=190 crops/step (CPU oracle port of the reference path)'},
+           'cpu_baseline': r, 'e2e': {'value': v, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

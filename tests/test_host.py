@@ -1,0 +1,120 @@
+"""CPU-only tests of the host logic and the C-ABI surface (no compute calls: there is no GPU in the build container)."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from aphantasia_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'aphb200.h')).read()
+    declared = sorted(set(re.findall(r'\b(aph_[a-z0-9_]+)\s*\(', hdr)))
+    assert len(declared) >= 20
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), 'libaphb200.so does not export %s' % name
+    assert sorted(_lib.EXPORTS) == declared, 'ctypes signature table and header disagree'
+    assert lib.aph_version() == 1
+    assert int(re.search(r'#define APH_CROP_PARAM_FLOATS (\d+)', hdr).group(1)) == __import__('aphantasia_b200._rng', fromlist=['x']).CROP_PARAM_FLOATS
+
+
+def test_table_layout_matches_header():
+    from aphantasia_b200 import _rng
+    hdr = open(os.path.join(ROOT, 'include', 'aphb200.h')).read()
+    get = lambda n: int(re.search(r'#define %s\s+(\d+)' % n, hdr).group(1))
+    assert (get('APH_F_OFFY'), get('APH_F_OFFX'), get('APH_F_CSIZE'), get('APH_F_FLAGS')) == (_rng.F_OFFY, _rng.F_OFFX, _rng.F_CSIZE, _rng.F_FLAGS)
+    assert (get('APH_F_PERSP'), get('APH_F_ER_I'), get('APH_F_ER_W'), get('APH_F_ROT'), get('APH_F_ANGLE')) == \
+           (_rng.F_PERSP, _rng.F_ER_I, _rng.F_ER_W, _rng.F_ROT, _rng.F_ANGLE)
+    assert (get('APH_TF_NONE'), get('APH_TF_NORMALIZE'), get('APH_TF_FAST')) == (_rng.TF_NONE, _rng.TF_NORMALIZE, _rng.TF_FAST)
+
+
+@pytest.mark.parametrize('count,world', [(190, 8), (87, 4), (190, 1), (3, 2), (5, 8), (47, 3)])
+def test_shard_range_is_a_balanced_partition(count, world):
+    from aphantasia_b200 import _rng
+    spans = [_rng.shard_range(count, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == count
+    assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+    sizes = [hi - lo for lo, hi in spans]
+    assert max(sizes) - min(sizes) <= 1
+    if (count, world) == (190, 8): assert sizes == [24] * 6 + [23] * 2
+    if (count, world) == (87, 4): assert sizes == [22, 22, 22, 21]
+
+
+def test_perspective_and_rotation_helpers_match_torchvision():
+    import torchvision.transforms.functional as TF
+    from aphantasia_b200 import _rng
+    start = [[0, 0], [223, 0], [223, 223], [0, 223]]
+    end = [[11, 30], [200, 5], [190, 215], [20, 199]]
+    assert _rng.perspective_coeffs(start, end) == TF._get_perspective_coeffs(start, end)
+    for ang in (-30., -7., 0., 13., 29.):
+        m = TF._get_inverse_affine_matrix([0., 0.], ang, [0., 0.], 1., [0., 0.])
+        assert _rng.inverse_rotation_matrix(ang) == [m[0], m[1], m[3], m[4]]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the loud failure on a GPU-less host')
+def test_product_path_has_no_cpu_fallback():
+    from aphantasia_b200 import transforms
+    from aphantasia_b200.utils import slice_imgs
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        slice_imgs([torch.rand(1, 3, 64, 64)], 2, 32, transforms.transforms_fast)
+    with pytest.raises(NotImplementedError):
+        slice_imgs([torch.rand(1, 3, 64, 64)], 2, 32, lambda x: x)
+
+
+def test_dropin_module_names_resolve():
+    sys.path.insert(0, os.path.join(ROOT, 'dropin'))
+    try:
+        for k in [k for k in sys.modules if k == 'aphantasia' or k.startswith('aphantasia.') or k in ('clip', 'imageio', 'lpips')]:
+            del sys.modules[k]
+        from aphantasia.image import to_valid_rgb, fft_image, dwt_image  # noqa: F401
+        from aphantasia.utils import (slice_imgs, derivat, sim_func, aesthetic_model, basename, img_list, img_read, plot_text,  # noqa: F401
+                                      txt_clean, checkout, old_torch)
+        from aphantasia import transforms
+        from aphantasia.progress_bar import ProgressBar  # noqa: F401
+        import clip
+        assert hasattr(transforms, 'transforms_fast') and hasattr(transforms, 'normalize') and hasattr(transforms, 'transforms_custom')
+        assert clip.tokenize('red square').shape == (1, 77)
+    finally:
+        sys.path.remove(os.path.join(ROOT, 'dropin'))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    from aphantasia_b200 import _dist, _rng
+    torch.manual_seed(100 + rank); np.random.seed(100 + rank)      # deliberately different before the seed sync
+    st = _dist.init()
+    S = 11
+    tabs, _ = _rng.draw_crop_table(S, (96, 128), 32, _rng.TF_FAST, 'uniform', 0.4)
+    lo, hi = _rng.shard_range(S, st['rank'], st['world'])
+    # stand-in for the per-crop canvas gradients: g_s = f(table row); local mean over the shard, weighted, summed over ranks
+    per_crop = torch.tensor(tabs[0][:, :3].sum(1) + tabs[0][:, 16], dtype=torch.float64)
+    local = per_crop[lo:hi].mean() if hi > lo else torch.zeros((), dtype=torch.float64)
+    g = (local * (hi - lo) / S).reshape(1).clone()
+    _dist.all_reduce_sum_(g)
+    q.put((rank, tabs[0].tobytes(), (lo, hi), float(g.item()), float(per_crop.mean().item())))
+    torch.distributed.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_matches_single_process():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q, port = ctx.Queue(), _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs: p.join(30)
+    (r0, t0, s0, g0, m0), (r1, t1, s1, g1, m1) = res
+    assert t0 == t1, 'ranks replayed different random streams'
+    assert s0 == (0, 6) and s1 == (6, 11)
+    assert abs(g0 - m0) < 1e-12 and abs(g1 - m0) < 1e-12        # weighted local means, summed == the global mean
