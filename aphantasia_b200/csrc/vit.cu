@@ -7,6 +7,8 @@
 // The residual stream is fp32; GEMM operands are bf16; every x_l is kept (out-of-place residual) so the
 // LayerNorm backward can recompute x-hat. No weight gradients (the reference computes and discards them).
 #include "vit_ops.cuh"
+#include "vit_attn_tc.cuh"
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include <map>
@@ -103,6 +105,13 @@ static int copy_f32(const float* src, float* dst, size_t n, cudaStream_t st) {
   }
 
 static inline int rows_grid(int rows) { return (rows * 32 + 255) / 256; }
+
+// APH_ATTN_SIMT=1 selects the fp32 SIMT attention kernels (debug / comparison); default = tensor-core kernels.
+static bool attn_simt() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("APH_ATTN_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 
 }  // namespace aph
 
@@ -254,8 +263,8 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
     APH_LAUNCH_OK();
     { GemmEpi ep; ep.bias = w.b_qkv; ep.out_bf16 = v->qkv[l];
       if ((e = launch_gemm(v->ln_out, w.w_qkv, GemmShape{M, 3 * D, D}, ep, st))) return e; }
-    k_attn_fwd<<<S * H, 256, attn_fwd_smem(T), st>>>(v->qkv[l], v->attn_out, T, D, H);
-    APH_LAUNCH_OK();
+    if (attn_simt()) { k_attn_fwd<<<S * H, 256, attn_fwd_smem(T), st>>>(v->qkv[l], v->attn_out, T, D, H); APH_LAUNCH_OK(); }
+    else if ((e = attn_dispatch(true, v->qkv[l], nullptr, v->attn_out, S, T, D, H, st))) return e;
     { GemmEpi ep; ep.bias = w.b_o; ep.resid = x_in; ep.out_f32 = x_mid;
       if ((e = launch_gemm(v->attn_out, w.w_o, GemmShape{M, D, D}, ep, st))) return e; }
     NCH_DISPATCH(D, k_ln_fwd<NCH><<<rows_grid(M), 256, 0, st>>>(x_mid, (size_t)D, w.ln2_w, w.ln2_b, v->ln_out, mean2, rstd2, M, D));
@@ -314,8 +323,8 @@ extern "C" int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* gr
     // attention branch: d_attn = dx . W_o; (dq,dk,dv) = attn'(...); d_ln1 = d_qkv . W_qkv
     { GemmEpi ep; ep.out_bf16 = v->d_attn;
       if ((e = launch_gemm(v->dx_bf, w.w_o_t, GemmShape{M, D, D}, ep, st))) return e; }
-    k_attn_bwd<<<S * H, 256, attn_bwd_smem(T), st>>>(v->qkv[l], v->d_attn, v->d_qkv, T, D, H);
-    APH_LAUNCH_OK();
+    if (attn_simt()) { k_attn_bwd<<<S * H, 256, attn_bwd_smem(T), st>>>(v->qkv[l], v->d_attn, v->d_qkv, T, D, H); APH_LAUNCH_OK(); }
+    else if ((e = attn_dispatch(false, v->qkv[l], v->d_attn, v->d_qkv, S, T, D, H, st))) return e;
     { GemmEpi ep; ep.out_f32 = v->d_ln;
       if ((e = launch_gemm(v->d_qkv, w.w_qkv_t, GemmShape{M, D, 3 * D}, ep, st))) return e; }
     NCH_DISPATCH(D, k_ln_bwd<NCH><<<rows_grid(M), 256, 0, st>>>(v->d_ln, x_in, mean1, rstd1, w.ln1_w, v->dx, v->dx_bf, M, T, D, 0, 1));

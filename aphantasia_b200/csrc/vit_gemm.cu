@@ -1,6 +1,7 @@
 // vit_gemm.cu -- host side of the tcgen05 GEMM (tensor-map encoding, launch) + the exported test entry.
 #include "tc_gemm.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace aph {
 
@@ -57,6 +58,16 @@ int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi,
   APH_REQUIRE(A && B && shp.M > 0, "gemm: null operand or empty M");
   APH_REQUIRE(shp.K % GEMM_BK == 0 && shp.K > 0, "gemm: K=%d must be a positive multiple of %d", shp.K, GEMM_BK);
   APH_REQUIRE(shp.N % 128 == 0 && shp.N > 0, "gemm: N=%d must be a positive multiple of 128", shp.N);
+  // tile width: APH_GEMM_BN=128|256 forces one; default picks 256-wide tiles when N allows it and the grid still fills
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("APH_GEMM_BN"); forced = e ? atoi(e) : 0; }
+  bool wide = (shp.N % 256 == 0);
+  if (forced == 128) wide = false;
+  else if (forced != 256 && wide) {
+    const int mt = (shp.M + GEMM_BM - 1) / GEMM_BM;
+    wide = mt * (shp.N / 256) >= kNumSMs;          // small problems keep the finer 128-wide tiling
+  }
+  if (wide) return launch_cfg<256, 4>(A, B, shp, epi, st);
   return launch_cfg<128, 6>(A, B, shp, epi, st);
 }
 

@@ -294,13 +294,13 @@ def run_ours(args):
         'clocks': clk,
         'roofline': {'bound': 'tensor', 'kernel': 'k_gemm_bf16_tn (tcgen05, all %d launches of one step)' % gemm['launches'],
                      'achieved': gemm['tflops'], 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': gemm['tflops'] / peak_tf, 'traffic': None,
-                     'peak_source': peak_src, 'gemm_ms_per_step': gemm['ms'],
+                     'peak_source': peak_src, 'gemm_ms_per_step': gemm['ms'], 'per_shape_ms': gemm.get('per_shape_ms'),
                      'vit_step_frac': (flops_vit / (1e-3 * (stages.get('vit_fwd', 0) + stages.get('vit_bwd', 0)) + 1e-12)) / 1e12 / peak_tf},
         'stages_ms': {k: round(v, 4) for k, v in stages.items()},
     }
     if world == 1:
         try:
-            out['cpu_baseline'] = cpu_baseline_port(sample_S=4)
+            out['cpu_baseline'] = cpu_baseline_port(sample_S=16)
         except Exception as ex:      # the baseline must never take the bench line down
             out['cpu_baseline'] = {'value': None, 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': 'failed: %r' % (ex,)}
     print(json.dumps(out))
