@@ -95,6 +95,49 @@ def draw_fast(row, size):
 
 
 def draw_crop_table(count, canvas_hw, size=224, kind=TF_FAST, align='uniform', macro=0., n_imgs=1):
+    """Crop tables for one slice_imgs call: native replay (libaphb200.so: aph_rng_crop_tables) unless APH_RNG_PY=1;
+    draw_crop_table_py below is the executable specification both are tested against."""
+    import os
+    if os.environ.get('APH_RNG_PY', '0') == '1':
+        return draw_crop_table_py(count, canvas_hw, size, kind, align, macro, n_imgs)
+    return draw_crop_table_native(count, canvas_hw, size, kind, align, macro, n_imgs)
+
+
+def _frame(H, W, align):
+    if 'over' in align:
+        fh, fw = (2 * H, 2 * W) if align == 'overmax' else (int(1.5 * H), int(1.5 * W))
+    else:
+        fh, fw = H, W
+    return (fh - H) // 2, (fw - W) // 2, fh, fw
+
+
+def draw_crop_table_native(count, canvas_hw, size=224, kind=TF_FAST, align='uniform', macro=0., n_imgs=1):
+    """Same draws as draw_crop_table_py, but the per-crop loop continues both Mersenne-Twister streams in C."""
+    import ctypes as C
+    from ._lib import check, lib
+    H, W = int(canvas_hw[0]), int(canvas_hw[1])
+    rnd_size = torch.rand(count)
+    if align == 'central':
+        rnd_offx = torch.clip(torch.randn(count) * 0.2 + 0.5, 0., 1.)
+        rnd_offy = torch.clip(torch.randn(count) * 0.2 + 0.5, 0., 1.)
+    else:
+        rnd_offx = torch.rand(count)
+        rnd_offy = torch.rand(count)
+    pad_top, pad_left, fh, fw = _frame(H, W, align)
+    tstate = torch.get_rng_state()
+    name, key, pos, has_gauss, cached = np.random.get_state()
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    cpos = C.c_int32(int(pos))
+    tabs = np.empty((n_imgs, count, CROP_PARAM_FLOATS), dtype=np.float32)
+    check(lib().aph_rng_crop_tables(tstate.data_ptr(), tstate.numel(), key.ctypes.data, C.byref(cpos), rnd_size.data_ptr(), rnd_offx.data_ptr(),
+                                    rnd_offy.data_ptr(), count, H, W, fh, fw, size, kind, float(macro), n_imgs, tabs.ctypes.data),
+          'aph_rng_crop_tables')
+    torch.set_rng_state(tstate)
+    np.random.set_state((name, key, int(cpos.value), has_gauss, cached))
+    return [tabs[i] for i in range(n_imgs)], (pad_top, pad_left, fh, fw)
+
+
+def draw_crop_table_py(count, canvas_hw, size=224, kind=TF_FAST, align='uniform', macro=0., n_imgs=1):
     """Replays slice_imgs' draws (reference utils.py:218-254) for `n_imgs` canvases of equal size.
 
     Returns a list (one per input image) of float32 numpy tables [count, CROP_PARAM_FLOATS] and the

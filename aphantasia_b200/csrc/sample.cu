@@ -113,6 +113,26 @@ __device__ __forceinline__ float stageB(const float* __restrict__ A, const CropP
 __constant__ float c_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
 __constant__ float c_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
+// Per-CTA tap tables: the 4 bicubic taps (canvas offset, weight) of every output row and column, computed once
+// (size entries each) instead of per pixel; wrap-around ('over*' frames) is folded into the stored canvas index.
+struct TapTables { int* xo; float* xw; int* yo; float* yw; };
+__device__ __forceinline__ TapTables build_taps(float* base, const CropParams& p, int size, int H, int W, int pad_top, int pad_left, float scale) {
+  TapTables t;
+  t.xo = reinterpret_cast<int*>(base); t.xw = base + 4 * size; t.yo = reinterpret_cast<int*>(base + 8 * size); t.yw = base + 12 * size;
+  for (int k = threadIdx.x; k < 2 * size; k += blockDim.x) {
+    const bool isy = k >= size;
+    const int o = isy ? k - size : k;
+    int idx[4]; float w[4];
+    cubic_taps(o, scale, p.cs, idx, w);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (isy) { int y = p.oy + idx[a] - pad_top; y %= H; if (y < 0) y += H; t.yo[4 * o + a] = y * W; t.yw[4 * o + a] = w[a]; }
+      else { int x = p.ox + idx[a] - pad_left; x %= W; if (x < 0) x += W; t.xo[4 * o + a] = x; t.xw[4 * o + a] = w[a]; }
+    }
+  }
+  return t;
+}
+
 __global__ void __launch_bounds__(1024, 1)
 k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pad_left, const float* __restrict__ table,
              int size, int kind, float* __restrict__ out) {
@@ -122,46 +142,49 @@ k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pa
   const float* cch = canvas + (size_t)ch * H * W;
   const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
   const int n = size * size;
-  // ---- stage 1: bicubic resize into shared memory
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    const int i = idx / size, j = idx - i * size;
-    int iy[4], ix[4]; float wy[4], wx[4];
-    cubic_taps(i, scale, p.cs, iy, wy);
-    cubic_taps(j, scale, p.cs, ix, wx);
-    int cx[4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) { int x = p.ox + ix[b] - pad_left; x %= W; if (x < 0) x += W; cx[b] = x; }
-    float acc = 0.f;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      int y = p.oy + iy[a] - pad_top; y %= H; if (y < 0) y += H;
-      const float* r = cch + (size_t)y * W;
-      const float rowv = wx[0] * __ldg(r + cx[0]) + wx[1] * __ldg(r + cx[1]) + wx[2] * __ldg(r + cx[2]) + wx[3] * __ldg(r + cx[3]);
-      acc += wy[a] * rowv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const TapTables tt = build_taps(A + ((n + 3) & ~3), p, size, H, W, pad_top, pad_left, scale);
+  __syncthreads();
+  // ---- stage 1: bicubic resize into shared memory (warp = output row, lanes stride the columns)
+  for (int i = warp; i < size; i += nwarps) {
+    const int4 yo = *reinterpret_cast<const int4*>(tt.yo + 4 * i);
+    const float4 wy = *reinterpret_cast<const float4*>(tt.yw + 4 * i);
+    const float* r0 = cch + yo.x; const float* r1 = cch + yo.y; const float* r2 = cch + yo.z; const float* r3 = cch + yo.w;
+    for (int j = lane; j < size; j += 32) {
+      const int4 xo = *reinterpret_cast<const int4*>(tt.xo + 4 * j);
+      const float4 wx = *reinterpret_cast<const float4*>(tt.xw + 4 * j);
+      const float v0 = wx.x * __ldg(r0 + xo.x) + wx.y * __ldg(r0 + xo.y) + wx.z * __ldg(r0 + xo.z) + wx.w * __ldg(r0 + xo.w);
+      const float v1 = wx.x * __ldg(r1 + xo.x) + wx.y * __ldg(r1 + xo.y) + wx.z * __ldg(r1 + xo.z) + wx.w * __ldg(r1 + xo.w);
+      const float v2 = wx.x * __ldg(r2 + xo.x) + wx.y * __ldg(r2 + xo.y) + wx.z * __ldg(r2 + xo.z) + wx.w * __ldg(r2 + xo.w);
+      const float v3 = wx.x * __ldg(r3 + xo.x) + wx.y * __ldg(r3 + xo.y) + wx.z * __ldg(r3 + xo.z) + wx.w * __ldg(r3 + xo.w);
+      float acc = wy.x * v0;
+      acc += wy.y * v1; acc += wy.z * v2; acc += wy.w * v3;
+      A[i * size + j] = acc;
     }
-    A[idx] = acc;
   }
   __syncthreads();
   // ---- stages 2-5 by tap composition
   float* o = out + ((size_t)crop * 3 + ch) * n;
   const float mean = c_mean[ch], sd = c_std[ch];
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    float v;
-    if (kind == APH_TF_FAST) {
-      const int i = idx / size, j = idx - i * size;
-      const Bilin b = rot_taps(p, i, j, size);
-      const float mask = b.w00 + b.w01 + b.w10 + b.w11;
-      float s = 0.f;
-      if (b.w00 != 0.f) s += b.w00 * stageB(A, p, b.y0, b.x0, size);
-      if (b.w01 != 0.f) s += b.w01 * stageB(A, p, b.y0, b.x0 + 1, size);
-      if (b.w10 != 0.f) s += b.w10 * stageB(A, p, b.y0 + 1, b.x0, size);
-      if (b.w11 != 0.f) s += b.w11 * stageB(A, p, b.y0 + 1, b.x0 + 1, size);
-      v = s * mask;
-    } else {
-      v = A[idx];
+  for (int i = warp; i < size; i += nwarps) {
+    for (int j = lane; j < size; j += 32) {
+      const int idx = i * size + j;
+      float v;
+      if (kind == APH_TF_FAST) {
+        const Bilin b = rot_taps(p, i, j, size);
+        const float mask = b.w00 + b.w01 + b.w10 + b.w11;
+        float s = 0.f;
+        if (b.w00 != 0.f) s += b.w00 * stageB(A, p, b.y0, b.x0, size);
+        if (b.w01 != 0.f) s += b.w01 * stageB(A, p, b.y0, b.x0 + 1, size);
+        if (b.w10 != 0.f) s += b.w10 * stageB(A, p, b.y0 + 1, b.x0, size);
+        if (b.w11 != 0.f) s += b.w11 * stageB(A, p, b.y0 + 1, b.x0 + 1, size);
+        v = s * mask;
+      } else {
+        v = A[idx];
+      }
+      if (kind != APH_TF_NONE) v = (v - mean) / sd;
+      o[idx] = v;
     }
-    if (kind != APH_TF_NONE) v = (v - mean) / sd;
-    o[idx] = v;
   }
 }
 
@@ -186,20 +209,24 @@ k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int 
   const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
   const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
   const int n = size * size;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float* go = grad_out + ((size_t)crop * 3 + ch) * n;
   const float inv_sd = (kind != APH_TF_NONE) ? 1.f / c_std[ch] : 1.f;
+  const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
+  const TapTables tt = build_taps(gA + ((n + 3) & ~3), p, size, H, W, pad_top, pad_left, scale);
   if (kind == APH_TF_FAST) {
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = 0.f;
     __syncthreads();
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-      const int i = idx / size, j = idx - i * size;
-      const Bilin b = rot_taps(p, i, j, size);
-      const float g = go[idx] / c_std[ch] * (b.w00 + b.w01 + b.w10 + b.w11);
-      if (g == 0.f) continue;
-      if (b.w00 != 0.f) scatterB(gA, p, b.y0, b.x0, size, g * b.w00);
-      if (b.w01 != 0.f) scatterB(gA, p, b.y0, b.x0 + 1, size, g * b.w01);
-      if (b.w10 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0, size, g * b.w10);
-      if (b.w11 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0 + 1, size, g * b.w11);
+    for (int i = warp; i < size; i += nwarps) {
+      for (int j = lane; j < size; j += 32) {
+        const Bilin b = rot_taps(p, i, j, size);
+        const float g = go[i * size + j] / c_std[ch] * (b.w00 + b.w01 + b.w10 + b.w11);
+        if (g == 0.f) continue;
+        if (b.w00 != 0.f) scatterB(gA, p, b.y0, b.x0, size, g * b.w00);
+        if (b.w01 != 0.f) scatterB(gA, p, b.y0, b.x0 + 1, size, g * b.w01);
+        if (b.w10 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0, size, g * b.w10);
+        if (b.w11 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0 + 1, size, g * b.w11);
+      }
     }
   } else {
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = go[idx] * inv_sd;
@@ -207,24 +234,22 @@ k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int 
   __syncthreads();
   // ---- bicubic adjoint: scatter the 16 taps into the canvas gradient
   float* gc = grad_canvas + (size_t)ch * H * W;
-  const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    const float g = gA[idx];
-    if (g == 0.f) continue;
-    const int i = idx / size, j = idx - i * size;
-    int iy[4], ix[4]; float wy[4], wx[4];
-    cubic_taps(i, scale, p.cs, iy, wy);
-    cubic_taps(j, scale, p.cs, ix, wx);
-    int cx[4];
+  for (int i = warp; i < size; i += nwarps) {
+    const int4 yo = *reinterpret_cast<const int4*>(tt.yo + 4 * i);
+    const float4 wy = *reinterpret_cast<const float4*>(tt.yw + 4 * i);
+    for (int j = lane; j < size; j += 32) {
+      const float g = gA[i * size + j];
+      if (g == 0.f) continue;
+      const int4 xo = *reinterpret_cast<const int4*>(tt.xo + 4 * j);
+      const float4 wx = *reinterpret_cast<const float4*>(tt.xw + 4 * j);
+      const int yoff[4] = {yo.x, yo.y, yo.z, yo.w};
+      const float wya[4] = {wy.x, wy.y, wy.z, wy.w};
 #pragma unroll
-    for (int b = 0; b < 4; ++b) { int x = p.ox + ix[b] - pad_left; x %= W; if (x < 0) x += W; cx[b] = x; }
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      int y = p.oy + iy[a] - pad_top; y %= H; if (y < 0) y += H;
-      float* r = gc + (size_t)y * W;
-      const float gy = g * wy[a];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) atomicAdd(r + cx[b], gy * wx[b]);
+      for (int a = 0; a < 4; ++a) {
+        float* r = gc + yoff[a];
+        const float gy = g * wya[a];
+        atomicAdd(r + xo.x, gy * wx.x); atomicAdd(r + xo.y, gy * wx.y); atomicAdd(r + xo.z, gy * wx.z); atomicAdd(r + xo.w, gy * wx.w);
+      }
     }
   }
 }
@@ -235,7 +260,7 @@ using namespace aph;
 
 static int check_sample_args(const char* who, int H, int W, int S, int size, int kind) {
   APH_REQUIRE(H > 0 && W > 0 && S >= 0 && size > 0, "%s: bad shape H=%d W=%d S=%d size=%d", who, H, W, S, size);
-  APH_REQUIRE((size_t)size * size * sizeof(float) <= 227 * 1024, "%s: size=%d does not fit one CTA's shared memory (max 238)", who, size);
+  APH_REQUIRE(((size_t)size * size + 4 + 16 * (size_t)size) * sizeof(float) <= 227 * 1024, "%s: size=%d does not fit one CTA's shared memory (max 233)", who, size);
   APH_REQUIRE(kind >= APH_TF_NONE && kind <= APH_TF_FAST, "%s: unknown transform kind %d", who, kind);
   return 0;
 }
@@ -245,7 +270,7 @@ extern "C" int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, in
   if (int e = check_sample_args("aph_sample_fwd", H, W, S, size, kind)) return e;
   if (S == 0) return 0;
   APH_REQUIRE(canvas && table && out, "aph_sample_fwd: null pointer");
-  const size_t smem = (size_t)size * size * sizeof(float);
+  const size_t smem = ((size_t)size * size + 4 + 16 * (size_t)size) * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
     APH_CUDA_OK(cudaFuncSetAttribute(k_sample_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -263,7 +288,7 @@ extern "C" int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, 
   APH_CUDA_OK(cudaMemsetAsync(grad_canvas, 0, (size_t)3 * H * W * sizeof(float), (cudaStream_t)stream));
   if (S == 0) return 0;
   APH_REQUIRE(grad_out && table, "aph_sample_bwd: null pointer");
-  const size_t smem = (size_t)size * size * sizeof(float);
+  const size_t smem = ((size_t)size * size + 4 + 16 * (size_t)size) * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
     APH_CUDA_OK(cudaFuncSetAttribute(k_sample_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -133,7 +133,9 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;          // 4 epilogue warps x (32 rows x 128 B) transpose staging
+  static constexpr int EPI_BYTES = 4 * 32 * 128;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
 };
 
@@ -209,16 +211,18 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31
+    // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (one accumulator row per lane), transposes each
+    // 32x32 fp32 chunk through a swizzled shared-memory staging tile so that global traffic is row-contiguous
+    // (8 lanes x 16 B = one full 128 B line per row), then applies the fused epilogue on float4 groups.
     const int q = warp & 3;
+    uint8_t* stage = smem + L::EPI_OFFSET + q * (32 * 128);
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
       mbar_wait(&tfull_bar[as], aph_);
       tc_fence_after();
-      const int m = m_blk * GEMM_BM + q * 32 + lane;
-      const bool valid = m < shp.M;
+      const int m_base = m_blk * GEMM_BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -230,82 +234,55 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
-        if (!valid) continue;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)      // lane = row: write its 32 columns as 8 swizzled 16-byte chunks
+          *reinterpret_cast<uint4*>(stage + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        __syncwarp();
         const int col0 = n_blk * BN + c * 32;
-        const size_t rowoff = (size_t)m * shp.N + col0;
-        float v[32];
+        const int c4 = lane & 7, col = col0 + 4 * c4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (epi.bias) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (epi.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + i));
-            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          const int m = m_base + rr;
+          if (m >= shp.M) continue;
+          float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+          const size_t off = (size_t)m * shp.N + col;
+          v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+          if (epi.out_pre) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+            uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(epi.out_pre + off) = u;
           }
-        }
-        if (epi.out_pre) {
-          uint4* o = reinterpret_cast<uint4*>(epi.out_pre + rowoff);
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]), p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-            uint4 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-            u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-            o[i / 8] = u;
+          if (epi.act == 1) { v.x = quickgelu(v.x); v.y = quickgelu(v.y); v.z = quickgelu(v.z); v.w = quickgelu(v.w); }
+          if (epi.gelu_in) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(epi.gelu_in + off));
+            const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            v.x *= quickgelu_grad(h0.x); v.y *= quickgelu_grad(h0.y); v.z *= quickgelu_grad(h1.x); v.w *= quickgelu_grad(h1.y);
           }
-        }
-        if (epi.act == 1) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = quickgelu(v[i]);
-        }
-        if (epi.gelu_in) {
-          const uint4* hp = reinterpret_cast<const uint4*>(epi.gelu_in + rowoff);
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            const uint4 u = __ldg(hp + i / 8);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 h = __bfloat1622float2(h2[j]);
-              v[i + 2 * j] *= quickgelu_grad(h.x); v[i + 2 * j + 1] *= quickgelu_grad(h.y);
+          if (epi.resid) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(epi.resid + off));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          if (epi.out_f32) {
+            if (epi.unpatch_p > 0) {
+              const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
+              const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
+              const int ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
+              *reinterpret_cast<float4*>(epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px) = v;
+            } else {
+              *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
             }
           }
-        }
-        if (epi.resid) {
-          const float4* rp = reinterpret_cast<const float4*>(epi.resid + rowoff);
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = __ldg(rp + i / 4);
-            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+          if (epi.out_bf16) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+            uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(epi.out_bf16 + off) = u;
           }
         }
-        if (epi.out_f32) {
-          if (epi.unpatch_p > 0) {
-            const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
-            const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const int col = col0 + i, ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
-              float* o = epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px;
-              *reinterpret_cast<float4*>(o) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
-          } else {
-            float4* o = reinterpret_cast<float4*>(epi.out_f32 + rowoff);
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) o[i / 4] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          }
-        }
-        if (epi.out_bf16) {
-          uint4* o = reinterpret_cast<uint4*>(epi.out_bf16 + rowoff);
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i], v[i + 1]), p1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), p3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-            uint4 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-            u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-            o[i / 8] = u;
-          }
-        }
+        __syncwarp();                    // staging tile is reused by the next chunk
       }
     }
   }

@@ -188,13 +188,25 @@ def timed(fn, steps, warmup, dist_barrier):
     return e0.elapsed_time(e1) / 1e3
 
 
+def usable_cpus():
+    """CPUs this process may really use: affinity mask and cgroup quota, not the host's core count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = min(n, max(1, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return max(1, min(n, 64))      # beyond 64 threads the per-crop ops of the reference only lose to thread overhead
+
+
 def cpu_baseline_port(sample_S, threads=None):
     """Times the oracle port of the reference step on the host cores on a bounded sample (sample_S of the 190 crops,
     full 1280x720 canvas) and extrapolates linearly in the crop count; synth fwd/bwd is measured at full size."""
     from aphantasia_b200 import _rng
     from aphantasia_b200.clip import synthetic_visual_state_dict
     from oracle import restate as R
-    cores = threads or os.cpu_count() or 1
+    cores = threads or usable_cpus()
     torch.set_num_threads(cores)
     torch.manual_seed(0); np.random.seed(0)
     params = 0.01 * torch.randn(1, 3, H, W // 2 + 1, 2)
@@ -300,7 +312,7 @@ def run_ours(args):
     }
     if world == 1:
         try:
-            out['cpu_baseline'] = cpu_baseline_port(sample_S=16)
+            out['cpu_baseline'] = cpu_baseline_port(sample_S=8)
         except Exception as ex:      # the baseline must never take the bench line down
             out['cpu_baseline'] = {'value': None, 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': 'failed: %r' % (ex,)}
     print(json.dumps(out))

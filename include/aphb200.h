@@ -86,12 +86,22 @@ int aph_valid_rgb_bwd(const float* grad_out, const float* out, int64_t hw, const
  * (bilinear, zeros, x coverage) -> erase -> rotate (bilinear, zeros, x coverage) -> normalise.
  * canvas [3,H,W]; the sampling frame is the canvas wrap-padded by (pad_top, pad_left)
  * ('over*' aligns, utils.py:152-187; 0,0 otherwise); table: DEVICE [S, APH_CROP_PARAM_FLOATS];
- * out [S,3,size,size]. size*size*4 bytes must fit one CTA's shared memory (size <= 238).           */
+ * out [S,3,size,size]. size*size*4 bytes must fit one CTA's shared memory (size <= 233).           */
 int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, int pad_left,
                    const float* table, int S, int size, int kind, float* out, void* stream);
 /* grad_out [S,3,size,size] -> grad_canvas [3,H,W] (zeroed here, then accumulated).                 */
 int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, int pad_left,
                    const float* table, int S, int size, int kind, float* grad_canvas, void* stream);
+
+/* HOST function (no GPU work): exact native replay of the reference's per-crop random draws (utils.py:244-247,
+ * torchvision RandomPerspective/RandomErasing.get_params, transforms.py:75) continuing torch's CPU generator
+ * (torch_state = the torch.get_rng_state() blob, updated in place) and NumPy's legacy MT19937 (np_key[624], *np_pos,
+ * updated in place). rnd_size/offx/offy are the [count] vectors slice_imgs draws first (utils.py:222-228).
+ * Writes tables [n_imgs][count][APH_CROP_PARAM_FLOATS] (HOST memory).                                              */
+int aph_rng_crop_tables(uint8_t* torch_state, int64_t torch_state_bytes, uint32_t* np_key, int32_t* np_pos,
+                        const float* rnd_size, const float* rnd_offx, const float* rnd_offy, int count,
+                        int H, int W, int frame_h, int frame_w, int size, int kind, float macro, int n_imgs,
+                        float* tables);
 
 /* ================= L1: CLIP ViT-B image encoder ===============================================
  * Replaces clip.model.CLIP.encode_image / VisionTransformer.forward (third-party OpenAI clip; call
