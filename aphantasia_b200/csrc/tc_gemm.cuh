@@ -122,10 +122,18 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
 }
 
-__device__ __forceinline__ float quickgelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float quickgelu(float x) { return __fdividef(x, 1.f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float quickgelu_grad(float x) {
-  const float s = 1.f / (1.f + __expf(-1.702f * x));
+  const float s = __fdividef(1.f, 1.f + __expf(-1.702f * x));
   return s * (1.f + 1.702f * x * (1.f - s));
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
 }
 
 template <int BN, int STAGES>
@@ -139,7 +147,7 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool UNPATCH>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape shp, GemmEpi epi) {
   using L = GemmSmem<BN, STAGES>;
@@ -215,7 +223,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // 32x32 fp32 chunk through a swizzled shared-memory staging tile so that global traffic is row-contiguous
     // (8 lanes x 16 B = one full 128 B line per row), then applies the fused epilogue on float4 groups.
     const int q = warp & 3;
-    uint8_t* stage = smem + L::EPI_OFFSET + q * (32 * 128);
+    const uint32_t stage = smem_u32(smem + L::EPI_OFFSET + q * (32 * 128));
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
@@ -236,7 +244,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)      // lane = row: write its 32 columns as 8 swizzled 16-byte chunks
-          *reinterpret_cast<uint4*>(stage + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          sts128(stage + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
         __syncwarp();
         const int col0 = n_blk * BN + c * 32;
         const int c4 = lane & 7, col = col0 + 4 * c4;
@@ -247,7 +255,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int rr = it * 4 + (lane >> 3);
           const int m = m_base + rr;
           if (m >= shp.M) continue;
-          float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+          float4 v = lds128(stage + rr * 128 + ((c4 ^ (rr & 7)) << 4));
           const size_t off = (size_t)m * shp.N + col;
           v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
           if (epi.out_pre) {
@@ -267,7 +275,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
           }
           if (epi.out_f32) {
-            if (epi.unpatch_p > 0) {
+            if (UNPATCH) {
               const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
               const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
               const int ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;

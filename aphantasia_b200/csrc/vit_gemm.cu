@@ -36,12 +36,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int K, int box_
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool UNPATCH>
 static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES, UNPATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
   CUtensorMap ma, mb;
@@ -49,7 +49,7 @@ static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi
   if (int e = make_tmap_bf16(&mb, B, shp.N, shp.K, BN)) return e;
   const int tiles = ((shp.M + GEMM_BM - 1) / GEMM_BM) * (shp.N / BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  k_gemm_bf16_tn<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, shp, epi);
+  k_gemm_bf16_tn<BN, STAGES, UNPATCH><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, shp, epi);
   APH_LAUNCH_OK();
   return 0;
 }
@@ -67,8 +67,8 @@ int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi,
     const int mt = (shp.M + GEMM_BM - 1) / GEMM_BM;
     wide = mt * (shp.N / 256) >= kNumSMs;          // small problems keep the finer 128-wide tiling
   }
-  if (wide) return launch_cfg<256, 4>(A, B, shp, epi, st);
-  return launch_cfg<128, 6>(A, B, shp, epi, st);
+  if (epi.unpatch_p > 0) return wide ? launch_cfg<256, 4, true>(A, B, shp, epi, st) : launch_cfg<128, 6, true>(A, B, shp, epi, st);
+  return wide ? launch_cfg<256, 4, false>(A, B, shp, epi, st) : launch_cfg<128, 6, false>(A, B, shp, epi, st);
 }
 
 }  // namespace aph

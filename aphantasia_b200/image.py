@@ -157,7 +157,7 @@ def to_valid_rgb(image_f, colors=1., decorrelate=True):
     colmat = _color_matrix_host(colors) if decorrelate else None
 
     def inner(*args, **kwargs):
-        if isinstance(image_f, FFTImage):
+        if isinstance(image_f, (FFTImage, DWTImage)):
             shift = args[0] if len(args) > 0 else kwargs.get('shift', None)
             contrast = args[1] if len(args) > 1 else kwargs.get('contrast', 1.)
             return image_f.fused(shift, contrast, colmat, True)
@@ -165,6 +165,96 @@ def to_valid_rgb(image_f, colors=1., decorrelate=True):
     return inner
 
 
+class _SynthDWT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gen, contrast, colmat, sigmoid, *Ys):
+        for y in Ys:
+            require_cuda(y, 'wavelet parameters')
+        ys = [y.detach().contiguous().float() for y in Ys]
+        ho, wo = gen.out_hw
+        dev = ys[0].device
+        x_raw = torch.empty(3, ho, wo, device=dev, dtype=torch.float32)
+        out = torch.empty(1, 3, ho, wo, device=dev, dtype=torch.float32)
+        stats = torch.empty(4, device=dev, dtype=torch.float64)
+        ptrs = (C.c_void_p * len(ys))(*[y.data_ptr() for y in ys])
+        check(lib().aph_synth_dwt_fwd(gen.plan, ptrs, gen.scales_c, float(contrast), colmat, int(sigmoid), x_raw.data_ptr(), stats.data_ptr(),
+                                      out.data_ptr(), stream_ptr()), 'aph_synth_dwt_fwd')
+        ctx.gen, ctx.contrast, ctx.colmat, ctx.sigmoid, ctx.shapes = gen, float(contrast), colmat, int(sigmoid), [tuple(y.shape) for y in Ys]
+        ctx.save_for_backward(x_raw, stats, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x_raw, stats, out = ctx.saved_tensors
+        gen = ctx.gen
+        g = grad_out.contiguous().float()
+        grads = [torch.empty(sh, device=g.device, dtype=torch.float32) for sh in ctx.shapes]
+        ptrs = (C.c_void_p * len(grads))(*[t.data_ptr() for t in grads])
+        check(lib().aph_synth_dwt_bwd(gen.plan, g.data_ptr(), out.data_ptr(), x_raw.data_ptr(), stats.data_ptr(), gen.scales_c, ctx.contrast,
+                                      ctx.colmat, ctx.sigmoid, ptrs, stream_ptr()), 'aph_synth_dwt_bwd')
+        return (None, None, None, None) + tuple(grads)
+
+
+class DWTImage:
+    """The `image_f` closure of dwt_image (image.py:66-69) as a callable object (fusable by to_valid_rgb)."""
+
+    def __init__(self, shape, wave, sharp):
+        from ._wavelets import reconstruction_filters
+        h, w = int(shape[2]), int(shape[3])
+        rec_lo, rec_hi = reconstruction_filters(wave)
+        L = len(rec_lo)
+        plan = C.c_void_p()
+        check(lib().aph_dwt_plan_create(C.byref(plan), h, w, (C.c_float * L)(*rec_lo), (C.c_float * L)(*rec_hi), L), 'aph_dwt_plan_create')
+        self.plan = plan
+        J = C.c_int()
+        dims = (C.c_int * 32)(); ohw = (C.c_int * 2)()
+        check(lib().aph_dwt_plan_levels(plan, C.byref(J), dims, ohw), 'aph_dwt_plan_levels')
+        self.J = J.value
+        self.level_hw = [(dims[2 * i], dims[2 * i + 1]) for i in range(self.J)]
+        self.out_hw = (ohw[0], ohw[1])
+        h0, w0 = self.level_hw[0]
+        self.scales = [((h0 * w0) / (hh * ww)) ** (1. - sharp) for (hh, ww) in self.level_hw]      # image.py:73-80
+        self.scales_c = (C.c_float * self.J)(*[float(v) for v in self.scales])
+        self.Ys = None
+
+    def param_shapes(self):
+        hJ, wJ = self.level_hw[-1]
+        return [(1, 3, hJ, wJ)] + [(1, 3, 3, hh, ww) for (hh, ww) in self.level_hw]
+
+    def __del__(self):
+        try:
+            if getattr(self, 'plan', None):
+                lib().aph_dwt_plan_destroy(self.plan)
+        except Exception:
+            pass
+
+    def fused(self, shift, contrast, colmat, sigmoid):
+        return _SynthDWT.apply(self, contrast, colmat, sigmoid, *self.Ys)
+
+    def __call__(self, shift=None, contrast=1.):
+        return self.fused(shift, contrast, None, False)
+
+
 def dwt_image(shape, wave='coif2', sharp=0.3, colors=1., resume=None):
-    """image.py:61-71 (DWT parameterisation, BASELINE config 3). Not built yet in this round."""
-    raise NotImplementedError('aphantasia_b200: dwt_image (SURVEY.md section 8a row a4) is not implemented yet; use FFT (default)')
+    """Drop-in for image.py:61-71 / init_dwt :33-59: returns (Ys, image_f, size) with Ys = [Yl, Yh_1 (finest) .. Yh_J]
+    ~ N(0,1) leaves. Resume from a .pt list / tensors is kept; image-file resume (img2dwt) is init-time, out of scope."""
+    _dist.init()
+    gen = DWTImage(shape, wave, sharp)
+    if resume is None:
+        Ys = [torch.randn(*sh) for sh in gen.param_shapes()]          # same draw order as init_dwt (image.py:42)
+        if _dist.world() > 1:
+            Ys = [y.cuda() for y in Ys]
+            for y in Ys: torch.distributed.broadcast(y, 0)
+        Ys = [y.cuda() for y in Ys]
+    elif isinstance(resume, str):
+        if not os.path.isfile(resume):
+            print(' Snapshot not found:', resume); exit()
+        if os.path.splitext(resume)[1].lower()[1:] in ['jpg', 'png', 'tif', 'bmp']:
+            raise NotImplementedError('aphantasia_b200: resuming from an image file (img2dwt) is not on the B200 hot path')
+        Ys = [y.detach().cuda() for y in torch.load(resume)]
+    else:
+        Ys = [y.cuda() for y in resume]
+    assert [tuple(y.shape) for y in Ys] == gen.param_shapes(), 'dwt_image: parameter shapes do not match this size / wavelet'
+    Ys = [y.requires_grad_(True) for y in Ys]
+    gen.Ys = Ys
+    return Ys, gen, None

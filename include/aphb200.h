@@ -75,6 +75,25 @@ int aph_synth_fft_bwd(aph_fft_plan* plan, const float* grad_out, const float* ou
                       const float* colmat_host, int apply_sigmoid,
                       float* grad_params, void* stream);
 
+/* Wavelet parameterisation (BASELINE config 3). Replaces dwt_image.inner (aphantasia/image.py:66-69):
+ *   img = DWTInverse((Yl, [Yh_i * scale_i])) * contrast / std, fused with to_valid_rgb like the FFT path.
+ * DWTInverse is pytorch_wavelets' (third-party, mode 'symmetric'); rec_lo / rec_hi (HOST, L taps) are the
+ * PyWavelets reconstruction filters. J = floor(log2(min(H, W))) levels (image.py:35-36).                        */
+typedef struct aph_dwt_plan aph_dwt_plan;
+int aph_dwt_plan_create(aph_dwt_plan** plan, int H, int W, const float* rec_lo_host, const float* rec_hi_host, int L);
+int aph_dwt_plan_destroy(aph_dwt_plan* plan);
+/* J; dims[2*i], dims[2*i+1] = band height/width of level i+1 (finest first); out_hw = synthesised image size      */
+int aph_dwt_plan_levels(const aph_dwt_plan* plan, int* J, int* dims, int* out_hw);
+/* Ys: HOST array of J+1 DEVICE pointers {Yl [3,hJ,wJ], Yh_1 [3,3,h1,w1] (finest), ..., Yh_J}; scales_host [J]
+ * (aphantasia/image.py:73-80). Outputs as aph_synth_fft_fwd (x_raw / out are [3,out_h,out_w]).                    */
+int aph_synth_dwt_fwd(aph_dwt_plan* plan, const float* const* Ys, const float* scales_host, float contrast,
+                      const float* colmat_host, int apply_sigmoid, float* x_raw, double* stats, float* out,
+                      void* stream);
+/* grad_Ys: HOST array of J+1 DEVICE pointers receiving d loss / d Ys (overwritten).                               */
+int aph_synth_dwt_bwd(aph_dwt_plan* plan, const float* grad_out, const float* out, const float* x_raw,
+                      double* stats, const float* scales_host, float contrast, const float* colmat_host,
+                      int apply_sigmoid, float* const* grad_Ys, void* stream);
+
 /* Stand-alone to_valid_rgb for a foreign image_f (aphantasia/image.py:21-28): img [3,H,W] -> out.  */
 int aph_valid_rgb_fwd(const float* img, int64_t hw, const float* colmat_host, float* out, void* stream);
 int aph_valid_rgb_bwd(const float* grad_out, const float* out, int64_t hw, const float* colmat_host,

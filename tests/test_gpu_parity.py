@@ -238,3 +238,27 @@ def test_full_step_config1_vs_oracle(L):
     assert _rel(emb, o_emb) < 2e-2
     assert abs(loss.item() - o_loss.item()) < 2e-3
     assert _rel(params[0].grad, o_grad) < 3e-2
+
+
+# ---------------------------------------------------------------------------------------------- DWT (config 3 generator)
+@pytest.mark.parametrize('h,w,wave', [(64, 96, 'db3'), (135, 240, 'db3'), (100, 100, 'db2'), (270, 480, 'haar')])
+def test_synth_dwt_vs_oracle(L, h, w, wave):
+    """dwt_image + to_valid_rgb vs the restated pytorch_wavelets DWTInverse (parity unpinned: third-party absent)."""
+    from aphantasia_b200.image import dwt_image, to_valid_rgb
+    _seed(h + w)
+    Ys, gen, _ = dwt_image([1, 3, h, w], wave, 0.3, 1.8, None)
+    rec_lo, rec_hi = R.wavelet_filters(wave)
+    assert [tuple(v) for v in R.dwt_level_shapes(h, w, len(rec_lo))] == gen.level_hw
+    rgb = to_valid_rgb(gen, colors=1.8)(contrast=1.1)
+    _seed(9)
+    cot = torch.randn(rgb.shape)
+    (rgb * cot.cuda()).sum().backward()
+    Yo = [y.detach().cpu().clone().requires_grad_(True) for y in Ys]
+    o_img = R.synth_dwt(Yo, rec_lo, rec_hi, 0.3, 1.1)
+    o_rgb = R.valid_rgb(o_img, R.color_matrix(1.8))
+    (o_rgb * cot).sum().backward()
+    assert tuple(rgb.shape) == tuple(o_rgb.shape)
+    assert _rel(gen(contrast=1.1), o_img) < 2e-5
+    assert _rel(rgb, o_rgb) < 2e-5
+    for a, b in zip(Ys, Yo):
+        assert _rel(a.grad, b.grad) < 2e-4
