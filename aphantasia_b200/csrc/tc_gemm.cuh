@@ -36,7 +36,20 @@ struct GemmShape { int M, N, K; };
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;       // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int GEMM_UK = 16;       // K per tcgen05.mma (kind::f16)
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;      // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue (2 per SM sub-partition)
+constexpr int GEMM_EPI_WARPS = 8;
+
+// compile-time epilogue kinds (a runtime-flag epilogue was instruction-latency bound: 1 warp per scheduler, long predicated body)
+enum : int {
+  EPI_F32 = 0,            // out_f32 = acc
+  EPI_BF16 = 1,           // out_bf16 = acc
+  EPI_BIAS_BF16 = 2,      // out_bf16 = acc + bias
+  EPI_BIAS_GELU = 3,      // out_pre = bf16(acc + bias); out_bf16 = quickgelu(acc + bias)
+  EPI_BIAS_RESID = 4,     // out_f32 = acc + bias + resid
+  EPI_GELUGRAD_BF16 = 5,  // out_bf16 = acc * quickgelu'(gelu_in)
+  EPI_UNPATCH = 6,        // out_f32[NCHW] = acc (patch-embed data gradient)
+  EPI_KINDS = 7
+};
 
 // ---- raw PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -128,11 +141,11 @@ __device__ __forceinline__ float quickgelu_grad(float x) {
   return s * (1.f + 1.702f * x * (1.f - s));
 }
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
 
@@ -142,12 +155,12 @@ struct GemmSmem {
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;          // 4 epilogue warps x (32 rows x 128 B) transpose staging
-  static constexpr int EPI_BYTES = 4 * 32 * 128;
+  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 32 * 128;
   static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
 };
 
-template <int BN, int STAGES, bool UNPATCH>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape shp, GemmEpi epi) {
   using L = GemmSmem<BN, STAGES>;
@@ -167,7 +180,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], GEMM_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -219,11 +232,12 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (one accumulator row per lane), transposes each
-    // 32x32 fp32 chunk through a swizzled shared-memory staging tile so that global traffic is row-contiguous
-    // (8 lanes x 16 B = one full 128 B line per row), then applies the fused epilogue on float4 groups.
-    const int q = warp & 3;
-    const uint32_t stage = smem_u32(smem + L::EPI_OFFSET + q * (32 * 128));
+    // ===== epilogue: 8 warps. Warp w reads TMEM lanes 32*(w%4) .. +31 (one accumulator row per lane) and owns the 32-column
+    // chunks c = half, half+2, ... (half = (w-4)/4). Each 32x32 fp32 chunk is transposed through a swizzled shared-memory tile
+    // so that global traffic is row-contiguous (8 lanes x 16 B = one 128 B line per row); the epilogue kind is compile-time.
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const uint32_t stage = smem_u32(smem + L::EPI_OFFSET + (warp - 4) * (32 * 128));
+    const int c4 = lane & 7, rsub = lane >> 3;
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
@@ -233,11 +247,11 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int m_base = m_blk * GEMM_BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_wait_ld();
-        if (c == BN / 32 - 1) {          // accumulator fully read: hand the TMEM stage back to the MMA warp
+        if (c + 2 >= BN / 32) {          // this warp's last read of the accumulator: hand the TMEM stage back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -246,51 +260,48 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int i = 0; i < 8; ++i)      // lane = row: write its 32 columns as 8 swizzled 16-byte chunks
           sts128(stage + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
         __syncwarp();
-        const int col0 = n_blk * BN + c * 32;
-        const int c4 = lane & 7, col = col0 + 4 * c4;
+        const int col = n_blk * BN + c * 32 + 4 * c4;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (epi.bias) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+        size_t off = (size_t)(m_base + rsub) * shp.N + col;
+        const size_t step = (size_t)4 * shp.N;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + (lane >> 3);
+        for (int it = 0; it < 8; ++it, off += step) {
+          const int rr = it * 4 + rsub;
           const int m = m_base + rr;
-          if (m >= shp.M) continue;
+          if (m >= shp.M) break;
           float4 v = lds128(stage + rr * 128 + ((c4 ^ (rr & 7)) << 4));
-          const size_t off = (size_t)m * shp.N + col;
-          v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-          if (epi.out_pre) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-            uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(epi.out_pre + off) = u;
-          }
-          if (epi.act == 1) { v.x = quickgelu(v.x); v.y = quickgelu(v.y); v.z = quickgelu(v.z); v.w = quickgelu(v.w); }
-          if (epi.gelu_in) {
-            const uint2 u = __ldg(reinterpret_cast<const uint2*>(epi.gelu_in + off));
-            const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-            const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-            v.x *= quickgelu_grad(h0.x); v.y *= quickgelu_grad(h0.y); v.z *= quickgelu_grad(h1.x); v.w *= quickgelu_grad(h1.y);
-          }
-          if (epi.resid) {
+          if (EPI == EPI_F32) {
+            *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
+          } else if (EPI == EPI_UNPATCH) {
+            const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
+            const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
+            const int ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
+            *reinterpret_cast<float4*>(epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px) = v;
+          } else if (EPI == EPI_BIAS_RESID) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(epi.resid + off));
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          }
-          if (epi.out_f32) {
-            if (UNPATCH) {
-              const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
-              const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
-              const int ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
-              *reinterpret_cast<float4*>(epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px) = v;
-            } else {
-              *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
+            v.x += bias4.x + b.x; v.y += bias4.y + b.y; v.z += bias4.z + b.z; v.w += bias4.w + b.w;
+            *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
+          } else {
+            if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+            if (EPI == EPI_BIAS_GELU) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+              uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+              *reinterpret_cast<uint2*>(epi.out_pre + off) = u;
+              v.x = quickgelu(v.x); v.y = quickgelu(v.y); v.z = quickgelu(v.z); v.w = quickgelu(v.w);
             }
-          }
-          if (epi.out_bf16) {
+            if (EPI == EPI_GELUGRAD_BF16) {
+              const uint2 u = __ldg(reinterpret_cast<const uint2*>(epi.gelu_in + off));
+              const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+              const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+              v.x *= quickgelu_grad(h0.x); v.y *= quickgelu_grad(h0.y); v.z *= quickgelu_grad(h1.x); v.w *= quickgelu_grad(h1.y);
+            }
             __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
             uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
             *reinterpret_cast<uint2*>(epi.out_bf16 + off) = u;
           }
         }
-        __syncwarp();                    // staging tile is reused by the next chunk
+        __syncwarp();                    // staging tile is reused by this warp's next chunk
       }
     }
   }

@@ -36,12 +36,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int K, int box_
   return 0;
 }
 
-template <int BN, int STAGES, bool UNPATCH>
+template <int BN, int STAGES, int EPI>
 static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES, UNPATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
   CUtensorMap ma, mb;
@@ -49,7 +49,7 @@ static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi
   if (int e = make_tmap_bf16(&mb, B, shp.N, shp.K, BN)) return e;
   const int tiles = ((shp.M + GEMM_BM - 1) / GEMM_BM) * (shp.N / BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  k_gemm_bf16_tn<BN, STAGES, UNPATCH><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, shp, epi);
+  k_gemm_bf16_tn<BN, STAGES, EPI><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, shp, epi);
   APH_LAUNCH_OK();
   return 0;
 }
@@ -67,8 +67,24 @@ int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi,
     const int mt = (shp.M + GEMM_BM - 1) / GEMM_BM;
     wide = mt * (shp.N / 256) >= kNumSMs;          // small problems keep the finer 128-wide tiling
   }
-  if (epi.unpatch_p > 0) return wide ? launch_cfg<256, 4, true>(A, B, shp, epi, st) : launch_cfg<128, 6, true>(A, B, shp, epi, st);
-  return wide ? launch_cfg<256, 4, false>(A, B, shp, epi, st) : launch_cfg<128, 6, false>(A, B, shp, epi, st);
+  // map the requested fusion onto one of the compiled epilogue kinds
+  int kind = -1;
+  const bool b = epi.bias, r = epi.resid, gi = epi.gelu_in, f = epi.out_f32, h = epi.out_bf16, pre = epi.out_pre, act = epi.act == 1, un = epi.unpatch_p > 0;
+  if (un && f && !b && !r && !gi && !h && !pre && !act) kind = EPI_UNPATCH;
+  else if (f && !h && !b && !r && !gi && !pre && !act) kind = EPI_F32;
+  else if (h && !f && !b && !r && !gi && !pre && !act) kind = EPI_BF16;
+  else if (h && !f && b && !r && !gi && !pre && !act) kind = EPI_BIAS_BF16;
+  else if (h && !f && b && !r && !gi && pre && act) kind = EPI_BIAS_GELU;
+  else if (f && !h && b && r && !gi && !pre && !act) kind = EPI_BIAS_RESID;
+  else if (h && !f && !b && !r && gi && !pre && !act) kind = EPI_GELUGRAD_BF16;
+  APH_REQUIRE(kind >= 0, "gemm: unsupported epilogue combination");
+#define APH_GEMM_CASE(K) case K: return wide ? launch_cfg<256, 4, K>(A, B, shp, epi, st) : launch_cfg<128, 6, K>(A, B, shp, epi, st);
+  switch (kind) {
+    APH_GEMM_CASE(EPI_F32) APH_GEMM_CASE(EPI_BF16) APH_GEMM_CASE(EPI_BIAS_BF16) APH_GEMM_CASE(EPI_BIAS_GELU)
+    APH_GEMM_CASE(EPI_BIAS_RESID) APH_GEMM_CASE(EPI_GELUGRAD_BF16) APH_GEMM_CASE(EPI_UNPATCH)
+  }
+#undef APH_GEMM_CASE
+  return 2;
 }
 
 }  // namespace aph
