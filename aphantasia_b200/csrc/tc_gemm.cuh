@@ -248,6 +248,23 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
+        // global operands of the fused epilogue are fetched FIRST (8 independent loads in flight per lane): issued inside
+        // the store loop they serialise behind the stores (possible aliasing) and the epilogue becomes load-latency bound
+        const int col = n_blk * BN + c * 32 + 4 * c4;
+        const size_t off0 = (size_t)(m_base + rsub) * shp.N + col;
+        const size_t step = (size_t)4 * shp.N;
+        float4 res4[EPI == EPI_BIAS_RESID ? 8 : 1];
+        uint2 gin[EPI == EPI_GELUGRAD_BF16 ? 8 : 1];
+        if (EPI == EPI_BIAS_RESID || EPI == EPI_GELUGRAD_BF16) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const bool ok = m_base + it * 4 + rsub < shp.M;
+            if (EPI == EPI_BIAS_RESID) res4[it] = ok ? __ldg(reinterpret_cast<const float4*>(epi.resid + off0 + it * step)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EPI == EPI_GELUGRAD_BF16) gin[it] = ok ? __ldg(reinterpret_cast<const uint2*>(epi.gelu_in + off0 + it * step)) : make_uint2(0u, 0u);
+          }
+        }
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_wait_ld();
@@ -260,11 +277,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int i = 0; i < 8; ++i)      // lane = row: write its 32 columns as 8 swizzled 16-byte chunks
           sts128(stage + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
         __syncwarp();
-        const int col = n_blk * BN + c * 32 + 4 * c4;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
-        size_t off = (size_t)(m_base + rsub) * shp.N + col;
-        const size_t step = (size_t)4 * shp.N;
+        size_t off = off0;
 #pragma unroll
         for (int it = 0; it < 8; ++it, off += step) {
           const int rr = it * 4 + rsub;
@@ -279,7 +292,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
             *reinterpret_cast<float4*>(epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px) = v;
           } else if (EPI == EPI_BIAS_RESID) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(epi.resid + off));
+            const float4 b = res4[EPI == EPI_BIAS_RESID ? it : 0];
             v.x += bias4.x + b.x; v.y += bias4.y + b.y; v.z += bias4.z + b.z; v.w += bias4.w + b.w;
             *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
           } else {
@@ -291,7 +304,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               v.x = quickgelu(v.x); v.y = quickgelu(v.y); v.z = quickgelu(v.z); v.w = quickgelu(v.w);
             }
             if (EPI == EPI_GELUGRAD_BF16) {
-              const uint2 u = __ldg(reinterpret_cast<const uint2*>(epi.gelu_in + off));
+              const uint2 u = gin[EPI == EPI_GELUGRAD_BF16 ? it : 0];
               const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
               const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
               v.x *= quickgelu_grad(h0.x); v.y *= quickgelu_grad(h0.y); v.z *= quickgelu_grad(h1.x); v.w *= quickgelu_grad(h1.y);

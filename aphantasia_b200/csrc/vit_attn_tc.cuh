@@ -90,10 +90,13 @@ __global__ void __launch_bounds__(NW * 32) k_attn_fwd_tc(const bf16* __restrict_
   const bf16* base = qkv + (size_t)s * T * ld + h * 64;
   load_tile64(Ks, base + D, ld, TK, T, NW * 32);
   load_tile64(Vs, base + 2 * D, ld, TK, T, NW * 32);
+  load_tile64(Qs, base, ld, QB, T, NW * 32);                 // first query block rides along with K / V
   const uint32_t ks_a = smem_u32(Ks), vs_a = smem_u32(Vs), qs_a = smem_u32(Qs);
   for (int q0 = 0; q0 < T; q0 += QB) {
-    __syncthreads();
-    load_tile64(Qs, base + (size_t)q0 * ld, ld, QB, T - q0, NW * 32);
+    if (q0 > 0) {
+      __syncthreads();
+      load_tile64(Qs, base + (size_t)q0 * ld, ld, QB, T - q0, NW * 32);
+    }
     __syncthreads();
     const int r0 = warp * 16;
     if (q0 + r0 >= T) continue;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(NW * 32) k_attn_fwd_tc(const bf16* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 template <int NW, int NT2>
-__global__ void __launch_bounds__(NW * 32) k_attn_bwd_tc(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1) k_attn_bwd_tc(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
                                                          int T, int D, int heads) {
   extern __shared__ __align__(128) uint8_t sm[];
   constexpr int TK = NT2 * 16, QB = NW * 16, KT = (NT2 + NW - 1) / NW, PB = ((TK + 63) / 64) * 128;
@@ -164,10 +167,14 @@ __global__ void __launch_bounds__(NW * 32) k_attn_bwd_tc(const bf16* __restrict_
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dv[i][j][0] = dv[i][j][1] = dv[i][j][2] = dv[i][j][3] = 0.f; dk[i][j][0] = dk[i][j][1] = dk[i][j][2] = dk[i][j][3] = 0.f; }
 
+  load_tile64(Qs, base, ld, QB, T, NW * 32);                 // first query block rides along with K / V
+  load_tile64(Gs, gbase, (size_t)D, QB, T, NW * 32);
   for (int q0 = 0; q0 < T; q0 += QB) {
-    __syncthreads();
-    load_tile64(Qs, base + (size_t)q0 * ld, ld, QB, T - q0, NW * 32);
-    load_tile64(Gs, gbase + (size_t)q0 * D, (size_t)D, QB, T - q0, NW * 32);
+    if (q0 > 0) {
+      __syncthreads();
+      load_tile64(Qs, base + (size_t)q0 * ld, ld, QB, T - q0, NW * 32);
+      load_tile64(Gs, gbase + (size_t)q0 * D, (size_t)D, QB, T - q0, NW * 32);
+    }
     __syncthreads();
     // ---------------- phase A: query rows r0 .. r0+15 of this block
     const int r0 = warp * 16;

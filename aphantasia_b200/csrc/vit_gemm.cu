@@ -1,6 +1,8 @@
 // vit_gemm.cu -- host side of the tcgen05 GEMM (tensor-map encoding, launch) + the exported test entry.
 #include "tc_gemm.cuh"
 #include <mutex>
+#include <vector>
+#include <utility>
 #include <stdlib.h>
 
 namespace aph {
@@ -36,6 +38,11 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int K, int box_
   return 0;
 }
 
+// ---- optional per-launch event timing (bench.py's roofline: the GEMM kernel's real time inside a step)
+static bool g_prof = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev;
+static std::vector<double> g_prof_flops;
+
 template <int BN, int STAGES, int EPI>
 static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
@@ -49,8 +56,11 @@ static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi
   if (int e = make_tmap_bf16(&mb, B, shp.N, shp.K, BN)) return e;
   const int tiles = ((shp.M + GEMM_BM - 1) / GEMM_BM) * (shp.N / BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
   k_gemm_bf16_tn<BN, STAGES, EPI><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, shp, epi);
   APH_LAUNCH_OK();
+  if (g_prof) { cudaEventRecord(e1, st); g_prof_ev.emplace_back(e0, e1); g_prof_flops.push_back(2.0 * shp.M * shp.N * shp.K); }
   return 0;
 }
 
@@ -96,4 +106,24 @@ extern "C" int aph_gemm_bf16_tn(const void* A, const void* B, float* C, int M, i
   GemmEpi epi;
   epi.out_f32 = C;
   return launch_gemm(A, B, GemmShape{M, N, K}, epi, (cudaStream_t)stream);
+}
+
+// Profiling aid for bench.py: enable=1 starts recording a CUDA-event pair around every GEMM launch (on its stream);
+// enable=0 stops, synchronises and returns the summed kernel time / FLOPs / launch count since it was enabled.
+extern "C" int aph_prof_gemm(int enable, double* total_ms, double* total_flops, int* launches) {
+  if (enable) { g_prof = true; g_prof_ev.clear(); g_prof_flops.clear(); return 0; }
+  g_prof = false;
+  double ms = 0., fl = 0.;
+  for (size_t i = 0; i < g_prof_ev.size(); ++i) {
+    APH_CUDA_OK(cudaEventSynchronize(g_prof_ev[i].second));
+    float t = 0.f;
+    APH_CUDA_OK(cudaEventElapsedTime(&t, g_prof_ev[i].first, g_prof_ev[i].second));
+    ms += t; fl += g_prof_flops[i];
+    cudaEventDestroy(g_prof_ev[i].first); cudaEventDestroy(g_prof_ev[i].second);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = (int)g_prof_ev.size();
+  g_prof_ev.clear(); g_prof_flops.clear();
+  return 0;
 }

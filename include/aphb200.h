@@ -156,6 +156,10 @@ int64_t aph_vit_bytes(const aph_vit* vit);
  * C[M,N] (fp32) = A[M,K] (bf16, row-major) . B[N,K]^T (bf16, row-major). K % 64 == 0, N % 128 == 0. */
 int aph_gemm_bf16_tn(const void* A, const void* B, float* C, int M, int N, int K, void* stream);
 
+/* Profiling aid: enable=1 records a CUDA-event pair around every GEMM launch of this library; enable=0 stops and returns
+ * the summed kernel time (ms), FLOPs (sum of 2MNK) and launch count since enabling (bench.py's roofline).            */
+int aph_prof_gemm(int enable, double* total_ms, double* total_flops, int* launches);
+
 /* ================= L1: similarity loss ========================================================
  * Replaces sim_func(v1, v2, type) for type in {None/'cossim', 'mix'} (aphantasia/utils.py:276-282,
  * 295). v1 [n1,D] with n1 in {1,S}; v2 [S,D]. value (device scalar) = mean_s f(v1, v2_s).
