@@ -18,6 +18,7 @@
 // Backward mirrors it: rotate/perspective adjoints scatter into a shared-memory gradient image
 // (shared atomics), then the bicubic adjoint scatters into the canvas gradient (global red.add).
 #include "aph_common.cuh"
+#include <stdlib.h>
 
 namespace aph {
 
@@ -254,6 +255,119 @@ k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Atomic-free backward for un-wrapped frames (the script's default 'uniform' / 'central' aligns).
+//   stage 1 (k_sample_bwd_stage1, transforms_fast only): rotate / erase / perspective adjoints per (crop, channel) in shared
+//            memory, result gA [S,3,size,size] written to a library scratch buffer (L2-resident at these sizes);
+//   stage 2 (k_sample_bwd_gather): one CTA owns a 16x64 canvas tile of one channel and walks the crops that cover it.
+//            The bicubic adjoint is separable: per (tile, crop) the <= 5 contributing output rows / columns and their
+//            weights (clamped border taps merged) are listed once, T = Wy^T gA is formed for the touched column range in
+//            shared memory, then each pixel reduces Wx^T T. Every canvas pixel is written exactly once: deterministic,
+//            no 457 M global atomics.
+__global__ void __launch_bounds__(1024, 1)
+k_sample_bwd_stage1(const float* __restrict__ grad_out, const float* __restrict__ table, int size, float* __restrict__ gA_out) {
+  extern __shared__ float gA[];
+  const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
+  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  const int n = size * size;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float* go = grad_out + ((size_t)crop * 3 + ch) * n;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = 0.f;
+  __syncthreads();
+  for (int i = warp; i < size; i += nwarps) {
+    for (int j = lane; j < size; j += 32) {
+      const Bilin b = rot_taps(p, i, j, size);
+      const float g = go[i * size + j] / c_std[ch] * (b.w00 + b.w01 + b.w10 + b.w11);
+      if (g == 0.f) continue;
+      if (b.w00 != 0.f) scatterB(gA, p, b.y0, b.x0, size, g * b.w00);
+      if (b.w01 != 0.f) scatterB(gA, p, b.y0, b.x0 + 1, size, g * b.w01);
+      if (b.w10 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0, size, g * b.w10);
+      if (b.w11 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0 + 1, size, g * b.w11);
+    }
+  }
+  __syncthreads();
+  float* o = gA_out + ((size_t)crop * 3 + ch) * n;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) o[idx] = gA[idx];
+}
+
+constexpr int GT_H = 16, GT_W = 64, GT_CAP = 8, GT_TW = 80;
+
+// lists the output indices whose (clamped) bicubic taps hit source index `rel`, with the summed weight
+__device__ __forceinline__ int adjoint_taps(int rel, float scale, int cs, int size, int* idx_out, float* w_out) {
+  int n = 0;
+  const int lo = max(0, (int)ceilf((float)(rel - 2) / scale) - 1);
+  const int hi = min(size - 1, (int)floorf((float)(rel + 2) / scale) + 1);
+  for (int i = lo; i <= hi; ++i) {
+    int idx[4]; float w[4];
+    cubic_taps(i, scale, cs, idx, w);
+    float ws = 0.f; bool hit = false;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) if (idx[a] == rel) { ws += w[a]; hit = true; }
+    if (hit && n < GT_CAP) { idx_out[n] = i; w_out[n] = ws; ++n; }
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(256)
+k_sample_bwd_gather(const float* __restrict__ gsrc, float pre_scale_r, float pre_scale_g, float pre_scale_b, const float* __restrict__ table,
+                    int S, int size, int H, int W, float* __restrict__ grad_canvas) {
+  __shared__ int rowcnt[GT_H], rowi[GT_H][GT_CAP], colcnt[GT_W], colj[GT_W][GT_CAP];
+  __shared__ float roww[GT_H][GT_CAP], colw[GT_W][GT_CAP], Tt[GT_H][GT_TW];
+  const int tiles_x = (W + GT_W - 1) / GT_W;
+  const int ch = blockIdx.y, y0 = (blockIdx.x / tiles_x) * GT_H, x0 = (blockIdx.x % tiles_x) * GT_W;
+  const int t = threadIdx.x, tx = t & (GT_W - 1), tyg = t >> 6;          // thread owns column tx, rows tyg + 4 r
+  const float pre = ch == 0 ? pre_scale_r : (ch == 1 ? pre_scale_g : pre_scale_b);
+  const int n = size * size;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int crop = 0; crop < S; ++crop) {
+    const float* row = table + (size_t)crop * APH_CROP_PARAM_FLOATS;
+    const int oy = (int)row[APH_F_OFFY], ox = (int)row[APH_F_OFFX], cs = (int)row[APH_F_CSIZE];
+    if (oy >= y0 + GT_H || oy + cs <= y0 || ox >= x0 + GT_W || ox + cs <= x0) continue;      // CTA-uniform
+    const float scale = (size > 1) ? (float)(cs - 1) / (float)(size - 1) : 0.f;
+    __syncthreads();
+    if (t < GT_H) {
+      const int rel = y0 + t - oy;
+      rowcnt[t] = (rel >= 0 && rel < cs && y0 + t < H) ? adjoint_taps(rel, scale, cs, size, rowi[t], roww[t]) : 0;
+    } else if (t >= 64 && t < 64 + GT_W) {
+      const int c = t - 64, rel = x0 + c - ox;
+      colcnt[c] = (rel >= 0 && rel < cs && x0 + c < W) ? adjoint_taps(rel, scale, cs, size, colj[c], colw[c]) : 0;
+    }
+    const int rx_lo = max(0, x0 - ox), rx_hi = min(cs - 1, x0 + GT_W - 1 - ox);
+    const int jlo = max(0, (int)ceilf((float)(rx_lo - 2) / scale) - 1);
+    const int jhi = min(size - 1, (int)floorf((float)(rx_hi + 2) / scale) + 1);
+    const int nj = min(jhi - jlo + 1, GT_TW);
+    __syncthreads();
+    const float* g = gsrc + ((size_t)crop * 3 + ch) * n + jlo;
+    for (int e = t; e < GT_H * nj; e += 256) {
+      const int ty = e / nj, jj = e - ty * nj;
+      float v = 0.f;
+      const int cnt = rowcnt[ty];
+      for (int a = 0; a < cnt; ++a) v += roww[ty][a] * __ldg(g + rowi[ty][a] * size + jj);
+      Tt[ty][jj] = v;
+    }
+    __syncthreads();
+    const int ccnt = colcnt[tx];
+    if (ccnt > 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int ty = tyg + 4 * r;
+        if (rowcnt[ty] > 0) {
+          float v = 0.f;
+          for (int b = 0; b < ccnt; ++b) v += colw[tx][b] * Tt[ty][colj[tx][b] - jlo];
+          acc[r] += v;
+        }
+      }
+    }
+  }
+  if (x0 + tx < W) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int y = y0 + tyg + 4 * r;
+      if (y < H) grad_canvas[((size_t)ch * H + y) * W + x0 + tx] = acc[r] * pre;
+    }
+  }
+}
+
 }  // namespace aph
 
 using namespace aph;
@@ -281,10 +395,49 @@ extern "C" int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, in
   return 0;
 }
 
+static float* g_gA = nullptr;          // stage-1 scratch [S,3,size,size] (library-owned: survives torch.cuda.empty_cache())
+static size_t g_gA_bytes = 0;
+
 extern "C" int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, int pad_left, const float* table, int S,
                               int size, int kind, float* grad_canvas, void* stream) {
   if (int e = check_sample_args("aph_sample_bwd", H, W, S, size, kind)) return e;
   APH_REQUIRE(grad_canvas, "aph_sample_bwd: null grad_canvas");
+  static int force_scatter = -1;
+  if (force_scatter < 0) { const char* e = getenv("APH_SAMPLE_BWD_SCATTER"); force_scatter = (e && e[0] == '1') ? 1 : 0; }
+  // (crops never upsample by more than 1/0.9 when min(H, W) >= size, which bounds the adjoint tap lists of the gather kernel)
+  if (S > 0 && pad_top == 0 && pad_left == 0 && !force_scatter && (H < W ? H : W) >= size) {
+    // ---- atomic-free path: (stage 1) + tile gather
+    APH_REQUIRE(grad_out && table, "aph_sample_bwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* gsrc = grad_out;
+    float pre[3] = {1.f, 1.f, 1.f};
+    if (kind == APH_TF_FAST) {
+      const size_t need = (size_t)S * 3 * size * size * sizeof(float);
+      if (need > g_gA_bytes) {
+        APH_CUDA_OK(cudaStreamSynchronize(st));
+        if (g_gA) cudaFree(g_gA);
+        g_gA = nullptr; g_gA_bytes = 0;
+        APH_CUDA_OK(cudaMalloc(&g_gA, need));
+        g_gA_bytes = need;
+      }
+      const size_t smem1 = (size_t)size * size * sizeof(float);
+      static size_t configured1 = 0;
+      if (smem1 > configured1) {
+        APH_CUDA_OK(cudaFuncSetAttribute(k_sample_bwd_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        configured1 = smem1;
+      }
+      k_sample_bwd_stage1<<<S * 3, 1024, smem1, st>>>(grad_out, table, size, g_gA);
+      APH_LAUNCH_OK();
+      gsrc = g_gA;
+    } else if (kind == APH_TF_NORMALIZE) {
+      const float sd[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+      for (int c = 0; c < 3; ++c) pre[c] = 1.f / sd[c];
+    }
+    dim3 grid(((W + GT_W - 1) / GT_W) * ((H + GT_H - 1) / GT_H), 3);
+    k_sample_bwd_gather<<<grid, 256, 0, st>>>(gsrc, pre[0], pre[1], pre[2], table, S, size, H, W, grad_canvas);
+    APH_LAUNCH_OK();
+    return 0;
+  }
   APH_CUDA_OK(cudaMemsetAsync(grad_canvas, 0, (size_t)3 * H * W * sizeof(float), (cudaStream_t)stream));
   if (S == 0) return 0;
   APH_REQUIRE(grad_out && table, "aph_sample_bwd: null pointer");

@@ -29,6 +29,7 @@ struct GemmEpi {
   int act = 0;                     // 1 = QuickGELU x*sigmoid(1.702x)
   int unpatch_p = 0;               // >0: out_f32 is [S,3,R,R]; row = s*g*g + gy*g + gx, col = c*p*p + py*p + px
   int unpatch_g = 0;
+  int nostore = 0;                 // profiling experiment: epilogue does everything but the global stores
 };
 
 struct GemmShape { int M, N, K; };
@@ -135,9 +136,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
 }
 
-__device__ __forceinline__ float quickgelu(float x) { return __fdividef(x, 1.f + __expf(-1.702f * x)); }
+// sigmoid(1.702 x) through ONE special-function op: 0.5 tanh(0.851 x) + 0.5 (tanh.approx: max rel. error 2^-11, far inside
+// the bf16 rounding of the value it feeds); the epilogues of the MLP GEMMs are MUFU-limited otherwise (exp + rcp per element)
+__device__ __forceinline__ float sigmoid1702(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float quickgelu(float x) { return x * sigmoid1702(x); }
 __device__ __forceinline__ float quickgelu_grad(float x) {
-  const float s = __fdividef(1.f, 1.f + __expf(-1.702f * x));
+  const float s = sigmoid1702(x);
   return s * (1.f + 1.702f * x * (1.f - s));
 }
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -285,6 +293,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (m >= shp.M) break;
           float4 v = lds128(stage + rr * 128 + ((c4 ^ (rr & 7)) << 4));
           if (EPI == EPI_F32) {
+            if (epi.nostore) { if (v.x == 1.2345e30f) epi.out_f32[0] = v.y; continue; }
             *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
           } else if (EPI == EPI_UNPATCH) {
             const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;

@@ -161,11 +161,14 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1) k_attn_bwd_tc(const 
   load_tile64(Ks, base + D, ld, TK, T, NW * 32);
   load_tile64(Vs, base + 2 * D, ld, TK, T, NW * 32);
   const uint32_t ks_a = smem_u32(Ks), vs_a = smem_u32(Vs), qs_a = smem_u32(Qs), gs_a = smem_u32(Gs), ps_a = smem_u32(Ps), ds_a = smem_u32(Ds);
+  constexpr bool ONE_BLOCK = (TK <= QB);       // all queries in one block (ViT-B/32): key-side accumulators only live in phase B
   float dv[KT][8][4], dk[KT][8][4];
+  if (!ONE_BLOCK) {
 #pragma unroll
-  for (int i = 0; i < KT; ++i)
+    for (int i = 0; i < KT; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { dv[i][j][0] = dv[i][j][1] = dv[i][j][2] = dv[i][j][3] = 0.f; dk[i][j][0] = dk[i][j][1] = dk[i][j][2] = dk[i][j][3] = 0.f; }
+      for (int j = 0; j < 8; ++j) { dv[i][j][0] = dv[i][j][1] = dv[i][j][2] = dv[i][j][3] = 0.f; dk[i][j][0] = dk[i][j][1] = dk[i][j][2] = dk[i][j][3] = 0.f; }
+  }
 
   load_tile64(Qs, base, ld, QB, T, NW * 32);                 // first query block rides along with K / V
   load_tile64(Gs, gbase, (size_t)D, QB, T, NW * 32);
@@ -182,6 +185,56 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1) k_attn_bwd_tc(const 
       uint32_t qa[4][4], ga[4][4];
       load_a_frags(qa, qs_a, r0, lane);
       load_a_frags(ga, gs_a, r0, lane);
+      float dq[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+      if (NT2 <= 4) {
+        // ---- register-resident variant: S and dP are computed once
+        float c[2 * NT2][4], e[2 * NT2][4];
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int n2 = 0; n2 < NT2; ++n2) {
+          qk_tile(c[2 * n2], c[2 * n2 + 1], qa, ks_a, n2 * 16, lane);
+          qk_tile(e[2 * n2], e[2 * n2 + 1], ga, vs_a, n2 * 16, lane);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int cl = n2 * 16 + u * 8 + 2 * t;
+            float* cc = c[2 * n2 + u];
+            cc[0] = (cl < T) ? cc[0] * kAttnScaleLog2 : -INFINITY; cc[1] = (cl + 1 < T) ? cc[1] * kAttnScaleLog2 : -INFINITY;
+            cc[2] = (cl < T) ? cc[2] * kAttnScaleLog2 : -INFINITY; cc[3] = (cl + 1 < T) ? cc[3] * kAttnScaleLog2 : -INFINITY;
+            m0 = fmaxf(m0, fmaxf(cc[0], cc[1])); m1 = fmaxf(m1, fmaxf(cc[2], cc[3]));
+          }
+        }
+        m0 = quad_max(m0); m1 = quad_max(m1);
+        float l0 = 0.f, l1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int n = 0; n < 2 * NT2; ++n) {
+          c[n][0] = exp2f(c[n][0] - m0); c[n][1] = exp2f(c[n][1] - m0); c[n][2] = exp2f(c[n][2] - m1); c[n][3] = exp2f(c[n][3] - m1);
+          l0 += c[n][0] + c[n][1]; l1 += c[n][2] + c[n][3];
+          d0 += c[n][0] * e[n][0] + c[n][1] * e[n][1]; d1 += c[n][2] * e[n][2] + c[n][3] * e[n][3];
+        }
+        l0 = quad_sum(l0); l1 = quad_sum(l1); d0 = quad_sum(d0); d1 = quad_sum(d1);
+        const float i0 = 1.f / l0, i1 = 1.f / l1;
+        d0 *= i0; d1 *= i1;
+#pragma unroll
+        for (int n2 = 0; n2 < NT2; ++n2) {
+          uint32_t pa[4], da[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float* cc = c[2 * n2 + u]; const float* ee = e[2 * n2 + u];
+            const float p0 = cc[0] * i0, p1 = cc[1] * i0, p2 = cc[2] * i1, p3 = cc[3] * i1;
+            pa[2 * u] = pack2(p0, p1); pa[2 * u + 1] = pack2(p2, p3);
+            da[2 * u] = pack2(p0 * (ee[0] - d0) * 0.125f, p1 * (ee[1] - d0) * 0.125f);
+            da[2 * u + 1] = pack2(p2 * (ee[2] - d1) * 0.125f, p3 * (ee[3] - d1) * 0.125f);
+            const int chunk = n2 * 2 + u;
+            *reinterpret_cast<uint32_t*>(Ps + swz(r0 + g, chunk, PB) + 4 * t) = pa[2 * u];
+            *reinterpret_cast<uint32_t*>(Ps + swz(r0 + g + 8, chunk, PB) + 4 * t) = pa[2 * u + 1];
+            *reinterpret_cast<uint32_t*>(Ds + swz(r0 + g, chunk, PB) + 4 * t) = da[2 * u];
+            *reinterpret_cast<uint32_t*>(Ds + swz(r0 + g + 8, chunk, PB) + 4 * t) = da[2 * u + 1];
+          }
+          av_step(dq, da, ks_a, n2 * 16, lane);
+        }
+      } else {
       // pass 1: row max and sum
       float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll 1
@@ -217,9 +270,6 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1) k_attn_bwd_tc(const 
       const float i0 = 1.f / l0, i1 = 1.f / l1;
       d0 *= i0; d1 *= i1;                        // delta_i = sum_j P_ij dP_ij
       // pass 3: P, dS (scaled by 1/8) -> smem (bf16) and dQ = dS K
-      float dq[8][4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
 #pragma unroll 1
       for (int n2 = 0; n2 < NT2; ++n2) {
         float c0[4], c1[4], e0[4], e1[4];
@@ -244,6 +294,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1) k_attn_bwd_tc(const 
         }
         av_step(dq, da, ks_a, n2 * 16, lane);
       }
+      }
       const int row0 = q0 + r0 + g, row1 = row0 + 8;
 #pragma unroll
       for (int dt = 0; dt < 8; ++dt) {
@@ -254,6 +305,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1) k_attn_bwd_tc(const 
     }
     __syncthreads();
     // ---------------- phase B: key tiles owned by this warp, reduced over the block's query rows
+    if (ONE_BLOCK) {
+#pragma unroll
+      for (int i = 0; i < KT; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dv[i][j][0] = dv[i][j][1] = dv[i][j][2] = dv[i][j][3] = 0.f; dk[i][j][0] = dk[i][j][1] = dk[i][j][2] = dk[i][j][3] = 0.f; }
+    }
 #pragma unroll
     for (int i = 0; i < KT; ++i) {
       const int kt = warp + i * NW;
@@ -303,6 +360,8 @@ static int attn_launch(bool fwd, const bf16* qkv, const bf16* dout, bf16* out_or
   if (!cfg) {
     APH_CUDA_OK(cudaFuncSetAttribute(k_attn_fwd_tc<NW, NT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc_fwd_smem<NW, NT2>()));
     APH_CUDA_OK(cudaFuncSetAttribute(k_attn_bwd_tc<NW, NT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc_bwd_smem<NW, NT2>()));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_attn_fwd_tc<NW, NT2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_attn_bwd_tc<NW, NT2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     cfg = true;
   }
   if (fwd) k_attn_fwd_tc<NW, NT2><<<S * heads, NW * 32, attn_tc_fwd_smem<NW, NT2>(), st>>>(qkv, out_or_dqkv, T, D, heads);

@@ -105,6 +105,7 @@ extern "C" int aph_gemm_bf16_tn(const void* A, const void* B, float* C, int M, i
   APH_REQUIRE(C != nullptr, "aph_gemm_bf16_tn: null output");
   GemmEpi epi;
   epi.out_f32 = C;
+  { const char* e = getenv("APH_GEMM_NOSTORE"); epi.nostore = (e && e[0] == '1') ? 1 : 0; }
   return launch_gemm(A, B, GemmShape{M, N, K}, epi, (cudaStream_t)stream);
 }
 
