@@ -402,8 +402,10 @@ extern "C" int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, 
                               int size, int kind, float* grad_canvas, void* stream) {
   if (int e = check_sample_args("aph_sample_bwd", H, W, S, size, kind)) return e;
   APH_REQUIRE(grad_canvas, "aph_sample_bwd: null grad_canvas");
+  // Measured on B200 (profiles/r1e): the atomic scatter (0.99 ms @ C2) beats this gather (1.85 ms: per-(tile, crop) list
+  // building + 3 barriers dominate), so the gather is opt-in: APH_SAMPLE_BWD_GATHER=1 gives a bit-reproducible gradient.
   static int force_scatter = -1;
-  if (force_scatter < 0) { const char* e = getenv("APH_SAMPLE_BWD_SCATTER"); force_scatter = (e && e[0] == '1') ? 1 : 0; }
+  if (force_scatter < 0) { const char* e = getenv("APH_SAMPLE_BWD_GATHER"); force_scatter = (e && e[0] == '1') ? 0 : 1; }
   // (crops never upsample by more than 1/0.9 when min(H, W) >= size, which bounds the adjoint tap lists of the gather kernel)
   if (S > 0 && pad_top == 0 && pad_left == 0 && !force_scatter && (H < W ? H : W) >= size) {
     // ---- atomic-free path: (stage 1) + tile gather

@@ -122,6 +122,31 @@ def test_sampler_vs_reference_golden(L, golden, name):
     assert _rel(canvas.grad[:, :, ::st, ::st], golden['smp_%s_gcanvas' % name]) < 1e-4
 
 
+def test_sampler_backward_gather_path_matches_scatter(L):
+    """The opt-in atomic-free backward (APH_SAMPLE_BWD_GATHER=1, separate process) equals the default scatter path."""
+    import os, subprocess, sys
+    code = """
+import torch, numpy as np, sys
+sys.path.insert(0, %r)
+from aphantasia_b200 import transforms
+from aphantasia_b200.utils import slice_imgs
+torch.manual_seed(11); np.random.seed(11)
+c = torch.rand(1, 3, 360, 640).cuda().requires_grad_(True)
+torch.manual_seed(5); np.random.seed(5)
+out = slice_imgs([c], 24, 224, transforms.transforms_fast, 'uniform', 0.4)[0]
+torch.manual_seed(6)
+(out * torch.randn(out.shape).cuda()).sum().backward()
+torch.save(c.grad.cpu(), sys.argv[1])
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ('0', '1'):
+        path = '/tmp/aph_gather_%s.pt' % flag
+        env = dict(os.environ, APH_SAMPLE_BWD_GATHER=flag)
+        subprocess.check_call([sys.executable, '-c', code, path], env=env)
+        outs.append(torch.load(path))
+    assert _rel(outs[1], outs[0]) < 1e-5
+
+
 @pytest.mark.parametrize('kind', [0, 1, 2])
 def test_sampler_vs_oracle_720p(L, kind):
     from aphantasia_b200 import _rng, transforms
