@@ -15,6 +15,9 @@ data-gradient -> sample bwd -> [all-reduce] -> synth bwd -> Adam.
           the pinned H2D copy of the crop table and a D2H read of the loss.
   --impl reference : the CPU oracle port of the reference path (oracle/restate.py) on the host cores.
 """
+import os as _os
+if _os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+    _os.environ['NCCL_DEBUG'] = 'WARN'          # NCCL's version banner goes to stdout: keep stdout to the one JSON line
 import argparse
 import ctypes as C
 import json
@@ -291,6 +294,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_api = float(t.item())
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peaks = {}

@@ -287,3 +287,63 @@ def test_synth_dwt_vs_oracle(L, h, w, wave):
     assert _rel(rgb, o_rgb) < 2e-5
     for a, b in zip(Ys, Yo):
         assert _rel(a.grad, b.grad) < 2e-4
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE full sizes
+@pytest.mark.parametrize('h,w', [(2160, 3840)])
+def test_synth_fft_4k_vs_oracle(L, h, w):
+    """Config 5 canvas (3840x2160): forward values and spectrum gradient vs the CPU oracle."""
+    _seed(1)
+    params = 0.01 * torch.randn(1, 3, h, w // 2 + 1, 2)
+    cot = torch.randn(1, 3, h, w)
+    img, rgb, grad = _run_synth(L, params.numpy(), h, w, 1.5, 1.8, 1.0, cot=cot.numpy())
+    p = params.clone().requires_grad_(True)
+    o_rgb = R.valid_rgb(R.synth_fft(p, R.fft_scale(h, w, 1.5), h, w), R.color_matrix(1.8))
+    (o_rgb * cot).sum().backward()
+    assert _rel(rgb, o_rgb) < 5e-5
+    assert _rel(grad, p.grad) < 3e-4
+
+
+def test_synth_dwt_config3_size_vs_oracle(L):
+    """Config 3 generator (db3, 1920x1080): values and wavelet-pyramid gradients vs the restated DWTInverse."""
+    from aphantasia_b200.image import dwt_image, to_valid_rgb
+    h, w = 1080, 1920
+    _seed(3)
+    Ys, gen, _ = dwt_image([1, 3, h, w], 'db3', 0.3, 1.8, None)
+    assert gen.level_hw[0] == (542, 962) and gen.level_hw[-1] == (6, 6) and gen.J == 10      # SURVEY.md 8a row a4
+    rgb = to_valid_rgb(gen, colors=1.8)()
+    _seed(4)
+    cot = torch.randn(rgb.shape)
+    (rgb * cot.cuda()).sum().backward()
+    rec_lo, rec_hi = R.wavelet_filters('db3')
+    Yo = [y.detach().cpu().clone().requires_grad_(True) for y in Ys]
+    o_rgb = R.valid_rgb(R.synth_dwt(Yo, rec_lo, rec_hi, 0.3, 1.0), R.color_matrix(1.8))
+    (o_rgb * cot).sum().backward()
+    assert _rel(rgb, o_rgb) < 5e-5
+    for a, b in zip(Ys, Yo):
+        assert _rel(a.grad, b.grad) < 3e-4
+
+
+def test_sampler_config5_shape_properties(L):
+    """4K canvas, ViT-B/16-sized batch shard (24 crops): size-independent properties of the fused sampler.
+    (i) linearity in the canvas, (ii) <grad, delta> == d/d eps of <cot, out(c + eps delta)> (adjoint identity)."""
+    from aphantasia_b200 import transforms
+    from aphantasia_b200.utils import slice_imgs
+    H, W, S = 2160, 3840, 24
+    _seed(2)
+    a = torch.rand(1, 3, H, W, device='cuda'); b = torch.rand(1, 3, H, W, device='cuda')
+
+    def run(c):
+        _seed(77)
+        return slice_imgs([c], S, 224, transforms.transforms_fast, 'uniform', 0.4)[0]
+    oa, ob, oab = run(a), run(b), run(2 * a - 3 * b)
+    mean = torch.tensor(R.CLIP_MEAN, device='cuda').view(1, 3, 1, 1); std = torch.tensor(R.CLIP_STD, device='cuda').view(1, 3, 1, 1)
+    un = lambda o: o * std + mean                   # undo the affine normalisation: what remains is linear in the canvas
+    assert _rel(un(oab), 2 * un(oa) - 3 * un(ob)) < 1e-4
+    c = a.clone().requires_grad_(True)
+    out = run(c)
+    cot = torch.randn_like(out)
+    (out * cot).sum().backward()
+    lhs = (c.grad * b).sum().item()
+    rhs = ((un(run(b)) * cot) / std).sum().item()    # <cot, L b> with L the linear part of the sampler
+    assert abs(lhs - rhs) < 1e-3 * abs(rhs)
