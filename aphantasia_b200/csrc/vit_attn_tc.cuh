@@ -12,6 +12,7 @@
 // bank-conflict free. qkv is bf16 [S*T, 3*D] (q | k | v), out / dout bf16 [S*T, D], dqkv bf16 [S*T, 3*D].
 #pragma once
 #include "tc_gemm.cuh"
+#include <stdlib.h>
 
 namespace aph {
 
@@ -348,6 +349,242 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1) k_attn_bwd_tc(const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pipelined variants for T <= 64 (ViT-B/32: T = 50): the per-(sample, head) problem is so small that a CTA is dominated by
+// the global-load latency of its 24-32 KB of operands (ncu: long-scoreboard stalls, 17 % warps active). Here a CTA walks a
+// strided list of (sample, head) items and prefetches the NEXT item's tiles with cp.async (zero-filled tail rows) into the
+// other half of a double buffer while it computes the current one.
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void load_tile64_async(uint32_t tile, const bf16* __restrict__ src, size_t ld, int rows, int valid, int nthreads) {
+  for (int idx = threadIdx.x; idx < rows * 8; idx += nthreads) {
+    const int r = idx >> 3, c = idx & 7;
+    const bool ok = r < valid;
+    cp_async16(tile + swz(r, c, 128), reinterpret_cast<const uint4*>(src + (size_t)(ok ? r : 0) * ld) + c, ok ? 16 : 0);
+  }
+}
+
+template <int NT2>
+__global__ void __launch_bounds__(128) k_attn_fwd_tc1(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int D, int heads, int items) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  constexpr int TK = NT2 * 16, QB = 64, BUF = (2 * TK + QB) * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const size_t ld = (size_t)3 * D;
+  auto issue = [&](int item, int b) {
+    const int s = item / heads, h = item - s * heads;
+    const bf16* base = qkv + (size_t)s * T * ld + h * 64;
+    const uint32_t a = smem_u32(sm + b * BUF);
+    load_tile64_async(a, base + D, ld, TK, T, 128);
+    load_tile64_async(a + TK * 128, base + 2 * D, ld, TK, T, 128);
+    load_tile64_async(a + 2 * TK * 128, base, ld, QB, T, 128);
+    cp_async_commit();
+  };
+  int item = blockIdx.x, b = 0;
+  if (item < items) issue(item, 0);
+  for (; item < items; item += gridDim.x, b ^= 1) {
+    const int nxt = item + gridDim.x;
+    if (nxt < items) { issue(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const int s = item / heads, h = item - s * heads;
+    const uint32_t ks_a = smem_u32(sm + b * BUF), vs_a = ks_a + TK * 128, qs_a = vs_a + TK * 128;
+    const int r0 = warp * 16;
+    if (r0 < T) {
+      uint32_t qa[4][4];
+      load_a_frags(qa, qs_a, r0, lane);
+      float c[2 * NT2][4];
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int n2 = 0; n2 < NT2; ++n2) {
+        qk_tile(c[2 * n2], c[2 * n2 + 1], qa, ks_a, n2 * 16, lane);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int col = n2 * 16 + u * 8 + 2 * t;
+          float* cc = c[2 * n2 + u];
+          cc[0] = (col < T) ? cc[0] * kAttnScaleLog2 : -INFINITY; cc[1] = (col + 1 < T) ? cc[1] * kAttnScaleLog2 : -INFINITY;
+          cc[2] = (col < T) ? cc[2] * kAttnScaleLog2 : -INFINITY; cc[3] = (col + 1 < T) ? cc[3] * kAttnScaleLog2 : -INFINITY;
+          m0 = fmaxf(m0, fmaxf(cc[0], cc[1])); m1 = fmaxf(m1, fmaxf(cc[2], cc[3]));
+        }
+      }
+      m0 = quad_max(m0); m1 = quad_max(m1);
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int n = 0; n < 2 * NT2; ++n) {
+        c[n][0] = exp2f(c[n][0] - m0); c[n][1] = exp2f(c[n][1] - m0); c[n][2] = exp2f(c[n][2] - m1); c[n][3] = exp2f(c[n][3] - m1);
+        l0 += c[n][0] + c[n][1]; l1 += c[n][2] + c[n][3];
+      }
+      l0 = quad_sum(l0); l1 = quad_sum(l1);
+      float o[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < NT2; ++kk) {
+        uint32_t pa[4] = {pack2(c[2 * kk][0], c[2 * kk][1]), pack2(c[2 * kk][2], c[2 * kk][3]),
+                          pack2(c[2 * kk + 1][0], c[2 * kk + 1][1]), pack2(c[2 * kk + 1][2], c[2 * kk + 1][3])};
+        av_step(o, pa, vs_a, kk * 16, lane);
+      }
+      const float i0 = 1.f / l0, i1 = 1.f / l1;
+      const int row0 = r0 + g, row1 = row0 + 8;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        const int col = h * 64 + dt * 8 + 2 * t;
+        if (row0 < T) *reinterpret_cast<__nv_bfloat162*>(out + ((size_t)s * T + row0) * D + col) = __floats2bfloat162_rn(o[dt][0] * i0, o[dt][1] * i0);
+        if (row1 < T) *reinterpret_cast<__nv_bfloat162*>(out + ((size_t)s * T + row1) * D + col) = __floats2bfloat162_rn(o[dt][2] * i1, o[dt][3] * i1);
+      }
+    }
+    __syncthreads();          // everyone is done with buffer b before the next-next prefetch overwrites it
+  }
+}
+
+template <int NT2>
+__global__ void __launch_bounds__(128, 2) k_attn_bwd_tc1(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
+                                                         int T, int D, int heads, int items) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  constexpr int TK = NT2 * 16, QB = 64, PB = 128, BUF = (2 * TK + 2 * QB) * 128;
+  uint8_t* Ps = sm + 2 * BUF; uint8_t* Ds = Ps + QB * PB;
+  const uint32_t ps_a = smem_u32(Ps), ds_a = smem_u32(Ds);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const size_t ld = (size_t)3 * D;
+  auto issue = [&](int item, int b) {
+    const int s = item / heads, h = item - s * heads;
+    const bf16* base = qkv + (size_t)s * T * ld + h * 64;
+    const uint32_t a = smem_u32(sm + b * BUF);
+    load_tile64_async(a, base + D, ld, TK, T, 128);
+    load_tile64_async(a + TK * 128, base + 2 * D, ld, TK, T, 128);
+    load_tile64_async(a + 2 * TK * 128, base, ld, QB, T, 128);
+    load_tile64_async(a + (2 * TK + QB) * 128, dout + (size_t)s * T * D + h * 64, (size_t)D, QB, T, 128);
+    cp_async_commit();
+  };
+  int item = blockIdx.x, b = 0;
+  if (item < items) issue(item, 0);
+  for (; item < items; item += gridDim.x, b ^= 1) {
+    const int nxt = item + gridDim.x;
+    if (nxt < items) { issue(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const int s = item / heads, h = item - s * heads;
+    bf16* obase = dqkv + (size_t)s * T * ld + h * 64;
+    const uint32_t ks_a = smem_u32(sm + b * BUF), vs_a = ks_a + TK * 128, qs_a = vs_a + TK * 128, gs_a = qs_a + QB * 128;
+    const int r0 = warp * 16;
+    {
+      uint32_t qa[4][4], ga[4][4];
+      load_a_frags(qa, qs_a, r0, lane);
+      load_a_frags(ga, gs_a, r0, lane);
+      float dq[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+      float c[2 * NT2][4], e[2 * NT2][4];
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int n2 = 0; n2 < NT2; ++n2) {
+        qk_tile(c[2 * n2], c[2 * n2 + 1], qa, ks_a, n2 * 16, lane);
+        qk_tile(e[2 * n2], e[2 * n2 + 1], ga, vs_a, n2 * 16, lane);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int cl = n2 * 16 + u * 8 + 2 * t;
+          float* cc = c[2 * n2 + u];
+          cc[0] = (cl < T) ? cc[0] * kAttnScaleLog2 : -INFINITY; cc[1] = (cl + 1 < T) ? cc[1] * kAttnScaleLog2 : -INFINITY;
+          cc[2] = (cl < T) ? cc[2] * kAttnScaleLog2 : -INFINITY; cc[3] = (cl + 1 < T) ? cc[3] * kAttnScaleLog2 : -INFINITY;
+          m0 = fmaxf(m0, fmaxf(cc[0], cc[1])); m1 = fmaxf(m1, fmaxf(cc[2], cc[3]));
+        }
+      }
+      m0 = quad_max(m0); m1 = quad_max(m1);
+      float l0 = 0.f, l1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int n = 0; n < 2 * NT2; ++n) {
+        c[n][0] = exp2f(c[n][0] - m0); c[n][1] = exp2f(c[n][1] - m0); c[n][2] = exp2f(c[n][2] - m1); c[n][3] = exp2f(c[n][3] - m1);
+        l0 += c[n][0] + c[n][1]; l1 += c[n][2] + c[n][3];
+        d0 += c[n][0] * e[n][0] + c[n][1] * e[n][1]; d1 += c[n][2] * e[n][2] + c[n][3] * e[n][3];
+      }
+      l0 = quad_sum(l0); l1 = quad_sum(l1); d0 = quad_sum(d0); d1 = quad_sum(d1);
+      const float i0 = 1.f / l0, i1 = 1.f / l1;
+      d0 *= i0; d1 *= i1;
+#pragma unroll
+      for (int n2 = 0; n2 < NT2; ++n2) {
+        uint32_t pa[4], da[4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float* cc = c[2 * n2 + u]; const float* ee = e[2 * n2 + u];
+          const float p0 = cc[0] * i0, p1 = cc[1] * i0, p2 = cc[2] * i1, p3 = cc[3] * i1;
+          pa[2 * u] = pack2(p0, p1); pa[2 * u + 1] = pack2(p2, p3);
+          da[2 * u] = pack2(p0 * (ee[0] - d0) * 0.125f, p1 * (ee[1] - d0) * 0.125f);
+          da[2 * u + 1] = pack2(p2 * (ee[2] - d1) * 0.125f, p3 * (ee[3] - d1) * 0.125f);
+          const int chunk = n2 * 2 + u;
+          *reinterpret_cast<uint32_t*>(Ps + swz(r0 + g, chunk, PB) + 4 * t) = pa[2 * u];
+          *reinterpret_cast<uint32_t*>(Ps + swz(r0 + g + 8, chunk, PB) + 4 * t) = pa[2 * u + 1];
+          *reinterpret_cast<uint32_t*>(Ds + swz(r0 + g, chunk, PB) + 4 * t) = da[2 * u];
+          *reinterpret_cast<uint32_t*>(Ds + swz(r0 + g + 8, chunk, PB) + 4 * t) = da[2 * u + 1];
+        }
+        av_step(dq, da, ks_a, n2 * 16, lane);
+      }
+      const int row0 = r0 + g, row1 = row0 + 8;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        const int col = dt * 8 + 2 * t;
+        if (row0 < T) *reinterpret_cast<__nv_bfloat162*>(obase + (size_t)row0 * ld + col) = __floats2bfloat162_rn(dq[dt][0], dq[dt][1]);
+        if (row1 < T) *reinterpret_cast<__nv_bfloat162*>(obase + (size_t)row1 * ld + col) = __floats2bfloat162_rn(dq[dt][2], dq[dt][3]);
+      }
+    }
+    __syncthreads();
+    if (warp < NT2) {          // key tile kt = warp
+      float dv[8][4], dk[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f; dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < QB / 16; ++ks) {
+        uint32_t pa[4], da[4];
+        const int srow = ks * 16 + (lane & 7) + ((lane >> 4) << 3), chunk = warp * 2 + ((lane >> 3) & 1);
+        ldsm4t(pa, ps_a + swz(srow, chunk, PB));
+        ldsm4t(da, ds_a + swz(srow, chunk, PB));
+        av_step(dv, pa, gs_a, ks * 16, lane);
+        av_step(dk, da, qs_a, ks * 16, lane);
+      }
+      const int key0 = warp * 16 + g, key1 = key0 + 8;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        const int col = dt * 8 + 2 * t;
+        if (key0 < T) {
+          *reinterpret_cast<__nv_bfloat162*>(obase + (size_t)key0 * ld + D + col) = __floats2bfloat162_rn(dk[dt][0], dk[dt][1]);
+          *reinterpret_cast<__nv_bfloat162*>(obase + (size_t)key0 * ld + 2 * D + col) = __floats2bfloat162_rn(dv[dt][0], dv[dt][1]);
+        }
+        if (key1 < T) {
+          *reinterpret_cast<__nv_bfloat162*>(obase + (size_t)key1 * ld + D + col) = __floats2bfloat162_rn(dk[dt][2], dk[dt][3]);
+          *reinterpret_cast<__nv_bfloat162*>(obase + (size_t)key1 * ld + 2 * D + col) = __floats2bfloat162_rn(dv[dt][2], dv[dt][3]);
+        }
+      }
+    }
+    __syncthreads();          // buffer b and Ps / Ds are free again
+  }
+}
+
+template <int NT2>
+static int attn_launch1(bool fwd, const bf16* qkv, const bf16* dout, bf16* out_or_dqkv, int S, int T, int D, int heads, cudaStream_t st) {
+  constexpr size_t smem_f = (size_t)2 * (2 * NT2 * 16 + 64) * 128;
+  constexpr size_t smem_b = (size_t)2 * (2 * NT2 * 16 + 128) * 128 + (size_t)2 * 64 * 128;
+  static bool cfg = false;
+  if (!cfg) {
+    APH_CUDA_OK(cudaFuncSetAttribute(k_attn_fwd_tc1<NT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_attn_bwd_tc1<NT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_attn_fwd_tc1<NT2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_attn_bwd_tc1<NT2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    cfg = true;
+  }
+  const int items = S * heads;
+  if (fwd) {
+    const int per_sm = (int)(220 * 1024 / smem_f) < 6 ? (int)(220 * 1024 / smem_f) : 6;
+    const int grid = items < kNumSMs * per_sm ? items : kNumSMs * per_sm;
+    k_attn_fwd_tc1<NT2><<<grid, 128, smem_f, st>>>(qkv, out_or_dqkv, T, D, heads, items);
+  } else {
+    const int per_sm = (int)(220 * 1024 / smem_b) < 3 ? (int)(220 * 1024 / smem_b) : 3;
+    const int grid = items < kNumSMs * per_sm ? items : kNumSMs * per_sm;
+    k_attn_bwd_tc1<NT2><<<grid, 128, smem_b, st>>>(qkv, dout, out_or_dqkv, T, D, heads, items);
+  }
+  APH_LAUNCH_OK();
+  return 0;
+}
+
 template <int NW, int NT2> constexpr size_t attn_tc_fwd_smem() { return (size_t)(2 * NT2 * 16 + NW * 16) * 128; }
 template <int NW, int NT2> constexpr size_t attn_tc_bwd_smem() {
   return (size_t)(2 * NT2 * 16 + 2 * NW * 16) * 128 + (size_t)2 * NW * 16 * (((NT2 * 16 + 63) / 64) * 128);
@@ -371,6 +608,10 @@ static int attn_launch(bool fwd, const bf16* qkv, const bf16* dout, bf16* out_or
 }
 
 static int attn_dispatch(bool fwd, const bf16* qkv, const bf16* dout, bf16* out_or_dqkv, int S, int T, int D, int heads, cudaStream_t st) {
+  static int nopipe = -1;
+  if (nopipe < 0) { const char* e = getenv("APH_ATTN_NOPIPE"); nopipe = (e && e[0] == '1') ? 1 : 0; }
+  if (!nopipe && T <= 32) return attn_launch1<2>(fwd, qkv, dout, out_or_dqkv, S, T, D, heads, st);
+  if (!nopipe && T <= 64) return attn_launch1<4>(fwd, qkv, dout, out_or_dqkv, S, T, D, heads, st);
   if (T <= 32) return attn_launch<4, 2>(fwd, qkv, dout, out_or_dqkv, S, T, D, heads, st);
   if (T <= 64) return attn_launch<4, 4>(fwd, qkv, dout, out_or_dqkv, S, T, D, heads, st);
   if (T <= 112) return attn_launch<8, 7>(fwd, qkv, dout, out_or_dqkv, S, T, D, heads, st);
