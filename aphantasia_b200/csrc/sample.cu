@@ -152,7 +152,10 @@ k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pa
   // load) in a per-warp strip, then every lane takes its 4 horizontal taps from the strip: ~3x fewer L1 wavefronts than 16
   // gathered loads per pixel. Wrapped frames and very wide spans (scale > ~3.8) use the direct 16-tap form.
   float* strip = A + ((n + 3) & ~3) + 16 * size + warp * STRIP;
-  const bool can_strip = (pad_top == 0 && pad_left == 0);
+  // measured on B200 (profiles/r1g): the strip form is SLOWER for the forward (0.68 vs 0.51 ms: two extra warp barriers and
+  // a dependent shared-memory round trip per chunk outweigh the saved L1 wavefronts) -> forward keeps the direct 16-tap form;
+  // the backward (where it removes 45 % of the global atomics) keeps the strip.
+  const bool can_strip = false && (pad_top == 0 && pad_left == 0);
   for (int i = warp; i < size; i += nwarps) {
     const int4 yo = *reinterpret_cast<const int4*>(tt.yo + 4 * i);
     const float4 wy = *reinterpret_cast<const float4*>(tt.yw + 4 * i);

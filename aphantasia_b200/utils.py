@@ -179,7 +179,41 @@ def basename(file):
     return os.path.splitext(os.path.basename(file))[0]
 
 
+# ---- preview write-out (clip_fft.py:297-306 runs it every `opt_step`, default every step): the JPEG encode of a
+# 1280x720 frame costs ~20-30 ms on the host -- several GPU steps. It is handed to a small thread pool so the optimisation
+# loop only pays for the array hand-over; readers of the output directory (img_list) and interpreter exit drain the queue.
+_pending = []
+_pool = None
+
+
+def _drain_saves():
+    while _pending:
+        _pending.pop(0).result()
+
+
+def _encode_save(fname, chw):
+    from imageio import imsave
+    img = np.transpose(chw, (1, 2, 0))
+    imsave(fname, np.clip(img * 255, 0, 255).astype(np.uint8))        # utils.py:98-100
+
+
+def _submit_save(fname, chw):
+    global _pool
+    if os.environ.get('APH_SYNC_SAVE', '0') == '1':
+        _encode_save(fname, chw)
+        return
+    if _pool is None:
+        import atexit
+        from concurrent.futures import ThreadPoolExecutor
+        _pool = ThreadPoolExecutor(max_workers=int(os.environ.get('APH_SAVE_THREADS', '4')))
+        atexit.register(_drain_saves)
+    while len(_pending) > 64:          # bound the queue (and host memory) if the encoder cannot keep up
+        _pending.pop(0).result()
+    _pending.append(_pool.submit(_encode_save, fname, chw))
+
+
 def img_list(path, subdir=None):
+    _drain_saves()
     if subdir is True:
         files = [os.path.join(dp, f) for dp, dn, fn in os.walk(path) for f in fn]
     else:
@@ -200,11 +234,8 @@ def img_read(path):
 
 def checkout(img, fname=None, verbose=False):
     """utils.py:94-100: CHW float -> HWC uint8 -> file (rank 0 only under torchrun). The cv2 preview is dropped."""
-    img = np.transpose(np.array(img)[:, :, :], (1, 2, 0))
     if fname is not None and _dist.rank() == 0:
-        from imageio import imsave
-        img = np.clip(img * 255, 0, 255).astype(np.uint8)
-        imsave(fname, img)
+        _submit_save(fname, np.array(img, dtype=np.float32))           # private copy; conversion + encode happen off-thread
 
 
 def derivat(img, mode='sobel'):
