@@ -137,6 +137,43 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) helpers: two CTAs of a cluster share one 256-row accumulator tile; each loads its own 128 rows
+// of A and HALF of the B tile, the leader issues the MMAs for both, tcgen05.commit multicasts the barrier arrivals.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() { asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to an mbarrier that may live in the peer (leader) CTA
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (after all previously issued MMAs retire) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO). sm_100 descriptor version 1.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -148,8 +185,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int m = GEMM_BM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // sigmoid(1.702 x) through ONE special-function op: 0.5 tanh(0.851 x) + 0.5 (tanh.approx: max rel. error 2^-11, far inside
@@ -173,10 +210,10 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return v;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG = 1>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;      // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;          // 4 epilogue warps x (32 rows x 128 B) transpose staging
   static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 32 * 128;
@@ -184,10 +221,10 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
 };
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int CG = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape shp, GemmEpi epi) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -197,19 +234,22 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (shp.M + GEMM_BM - 1) / GEMM_BM, n_tiles = shp.N / BN;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;      // position inside the CTA pair (0 = leader)
+  // a "tile" is one accumulator of (128*CG) x BN: with CG = 2 the pair shares it, each CTA owning 128 of its rows
+  const int m_tiles = (shp.M + GEMM_BM * CG - 1) / (GEMM_BM * CG), n_tiles = shp.N / BN;
   const int num_tiles = m_tiles * n_tiles, k_blocks = shp.K / GEMM_BK;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], GEMM_EPI_WARPS); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CG * GEMM_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) { if (CG == 2) tmem_alloc_cg2(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -218,24 +258,32 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ===== TMA producer
       const uint64_t pol_b = l2_policy_evict_last();      // B = weights: shared by all M tiles
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = (tile / n_tiles) * CG + (int)rank, n_blk = tile % n_tiles;
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-          tma_load_2d(sa, &map_a, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d_hint(sa + L::A_BYTES, &map_b, &full_bar[s], kb * GEMM_BK, n_blk * BN, pol_b);
+          if (CG == 2) {
+            // both CTAs credit the LEADER's full barrier: the leader's MMA consumes the stage of both
+            const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[s]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES); else mbar_arrive_cluster(lead_full);
+            tma_load_2d_2sm(sa, &map_a, lead_full, kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d_2sm(sa + L::A_BYTES, &map_b, lead_full, kb * GEMM_BK, n_blk * BN + (int)rank * (BN / 2));
+          } else {
+            mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+            tma_load_2d(sa, &map_a, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d_hint(sa + L::A_BYTES, &map_b, &full_bar[s], kb * GEMM_BK, n_blk * BN, pol_b);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer
-      constexpr uint32_t idesc = make_idesc_bf16(BN);
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (the leader CTA issues for the pair when CG = 2)
+      constexpr uint32_t idesc = make_idesc_bf16(BN, GEMM_BM * CG);
       uint32_t it = 0, tile_iter = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_iter) {
         const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph_ ^ 1);
         tc_fence_after();
@@ -249,10 +297,16 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < GEMM_BK / GEMM_UK; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (>>4) address field
-            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            if (CG == 2) umma_f16_cg2(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[s]);                   // smem stage free once these MMAs retire
-          if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);   // accumulator complete
+          if (CG == 2) {
+            umma_commit_mc(&empty_bar[s], 0b11);                          // both CTAs' smem stages are free
+            if (kb == k_blocks - 1) umma_commit_mc(&tfull_bar[as], 0b11);   // both CTAs' epilogues may read TMEM
+          } else {
+            umma_commit(&empty_bar[s]);                   // smem stage free once these MMAs retire
+            if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);   // accumulator complete
+          }
         }
       }
     }
@@ -264,8 +318,8 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t stage = smem_u32(smem + L::EPI_OFFSET + (warp - 4) * (32 * 128));
     const int c4 = lane & 7, rsub = lane >> 3;
     uint32_t tile_iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
-      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_iter) {
+      const int m_blk = (tile / n_tiles) * CG + (int)rank, n_blk = tile % n_tiles;
       const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
       mbar_wait(&tfull_bar[as], aph_);
       tc_fence_after();
@@ -296,7 +350,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (c + 2 >= BN / 32) {          // this warp's last read of the accumulator: hand the TMEM stage back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0)); else mbar_arrive(&tempty_bar[as]); }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)      // lane = row: write its 32 columns as 8 swizzled 16-byte chunks
@@ -344,9 +398,10 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   }
+  __syncwarp();               // single-lane roles rejoin their warp before the (warp-aligned) cluster barrier
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) { if (CG == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // ---- host side ---------------------------------------------------------------------------------

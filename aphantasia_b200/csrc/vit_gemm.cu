@@ -43,22 +43,33 @@ static bool g_prof = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev;
 static std::vector<double> g_prof_flops;
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int CG = 1>
 static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, CG>;
   static bool configured = false;
   if (!configured) {
-    APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
   CUtensorMap ma, mb;
   if (int e = make_tmap_bf16(&ma, A, shp.M, shp.K, GEMM_BM)) return e;
-  if (int e = make_tmap_bf16(&mb, B, shp.N, shp.K, BN)) return e;
-  const int tiles = ((shp.M + GEMM_BM - 1) / GEMM_BM) * (shp.N / BN);
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  if (int e = make_tmap_bf16(&mb, B, shp.N, shp.K, BN / CG)) return e;
+  const int tiles = ((shp.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * (shp.N / BN);
+  const int slots = kNumSMs / CG;
+  const int grid = CG * (tiles < slots ? tiles : slots);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
-  k_gemm_bf16_tn<BN, STAGES, EPI><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, shp, epi);
+  if (CG == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    APH_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_bf16_tn<BN, STAGES, EPI, CG>, ma, mb, shp, epi));
+  } else {
+    k_gemm_bf16_tn<BN, STAGES, EPI, CG><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, shp, epi);
+  }
   APH_LAUNCH_OK();
   if (g_prof) { cudaEventRecord(e1, st); g_prof_ev.emplace_back(e0, e1); g_prof_flops.push_back(2.0 * shp.M * shp.N * shp.K); }
   return 0;
@@ -88,7 +99,11 @@ int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi,
   else if (f && !h && b && r && !gi && !pre && !act) kind = EPI_BIAS_RESID;
   else if (h && !f && !b && !r && gi && !pre && !act) kind = EPI_GELUGRAD_BF16;
   APH_REQUIRE(kind >= 0, "gemm: unsupported epilogue combination");
-#define APH_GEMM_CASE(K) case K: return wide ? launch_cfg<256, 4, K>(A, B, shp, epi, st) : launch_cfg<128, 6, K>(A, B, shp, epi, st);
+  // APH_GEMM_2CTA=1: CTA-pair tiles (cta_group::2, 256 x 256 accumulator per pair, B tile split across the pair)
+  static int pair = -1;
+  if (pair < 0) { const char* e = getenv("APH_GEMM_2CTA"); pair = (e && e[0] == '1') ? 1 : 0; }
+  const bool use_pair = pair && wide && ((shp.M + 255) / 256) * (shp.N / 256) >= kNumSMs / 2;
+#define APH_GEMM_CASE(K) case K: return use_pair ? launch_cfg<256, 6, K, 2>(A, B, shp, epi, st) : (wide ? launch_cfg<256, 4, K>(A, B, shp, epi, st) : launch_cfg<128, 6, K>(A, B, shp, epi, st));
   switch (kind) {
     APH_GEMM_CASE(EPI_F32) APH_GEMM_CASE(EPI_BF16) APH_GEMM_CASE(EPI_BIAS_BF16) APH_GEMM_CASE(EPI_BIAS_GELU)
     APH_GEMM_CASE(EPI_BIAS_RESID) APH_GEMM_CASE(EPI_GELUGRAD_BF16) APH_GEMM_CASE(EPI_UNPATCH)
