@@ -99,9 +99,10 @@ int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi,
   else if (f && !h && b && r && !gi && !pre && !act) kind = EPI_BIAS_RESID;
   else if (h && !f && !b && !r && gi && !pre && !act) kind = EPI_GELUGRAD_BF16;
   APH_REQUIRE(kind >= 0, "gemm: unsupported epilogue combination");
-  // APH_GEMM_2CTA=1: CTA-pair tiles (cta_group::2, 256 x 256 accumulator per pair, B tile split across the pair)
+  // CTA-pair tiles (cta_group::2, 256 x 256 accumulator per pair, B tile split across the pair) are the default for large
+  // problems: measured +3 % steps/s at C2 (profiles/README.md). APH_GEMM_2CTA=0 forces single-CTA tiles.
   static int pair = -1;
-  if (pair < 0) { const char* e = getenv("APH_GEMM_2CTA"); pair = (e && e[0] == '1') ? 1 : 0; }
+  if (pair < 0) { const char* e = getenv("APH_GEMM_2CTA"); pair = (e && e[0] == '0') ? 0 : 1; }
   const bool use_pair = pair && wide && ((shp.M + 255) / 256) * (shp.N / 256) >= kNumSMs / 2;
 #define APH_GEMM_CASE(K) case K: return use_pair ? launch_cfg<256, 6, K, 2>(A, B, shp, epi, st) : (wide ? launch_cfg<256, 4, K>(A, B, shp, epi, st) : launch_cfg<128, 6, K>(A, B, shp, epi, st));
   switch (kind) {
