@@ -150,28 +150,43 @@ class DeviceStep:
         self._mark('adam')
 
 
+# supplementary workloads (BASELINE.json configs; effective crop counts after the script's multipliers)
+CONFIGS = {
+    'c1': dict(hw=(224, 224), S=3, patch=32, dwt=False, sim='mix', note='configs[0] shape: 224x224, --samples 4 -> S=3, ViT-B/32'),
+    'c2': dict(hw=(720, 1280), S=190, patch=32, dwt=False, sim='mix', note='configs[1]: 1280x720 FFT, --samples 200 -> S=190, ViT-B/32'),
+    'c3': dict(hw=(1080, 1920), S=47, patch=16, dwt=True, sim='mix', note='configs[2]: --dwt --wave db3 1920x1080, --samples 200 -> S=47, ViT-B/16'),
+    'c5shard': dict(hw=(2160, 3840), S=24, patch=16, dwt=False, sim='mix', note='configs[4], one rank of 8: 3840x2160 FFT, S=190 -> 24 crops/rank, ViT-B/16 (no all-reduce)'),
+}
+
+
 class ApiStep:
     """The same step through the reference-facing Python entry points (what clip_fft.py's train(i) executes)."""
 
-    def __init__(self, seed=0):
+    def __init__(self, seed=0, cfg=None):
         from aphantasia_b200 import transforms
         from aphantasia_b200.clip import CLIP, synthetic_visual_state_dict
-        from aphantasia_b200.image import fft_image, to_valid_rgb
+        from aphantasia_b200.image import dwt_image, fft_image, to_valid_rgb
         from aphantasia_b200.utils import sim_func, slice_imgs
+        cfg = cfg or CONFIGS['c2']
+        self.S, self.sim = cfg['S'], cfg['sim']
+        h, w = cfg['hw']
         self.slice_imgs, self.sim_func, self.tf = slice_imgs, sim_func, transforms.transforms_fast
         torch.manual_seed(seed); np.random.seed(seed)
-        self.params, image_f, _ = fft_image([1, 3, H, W], 0.07, 1.5, None)
+        if cfg['dwt']:
+            self.params, image_f, _ = dwt_image([1, 3, h, w], 'db3', 0.3, 1.8, None)
+        else:
+            self.params, image_f, _ = fft_image([1, 3, h, w], 0.07, 1.5, None)
         self.image_f = to_valid_rgb(image_f, colors=1.8)
-        self.model = CLIP(MODEL, synthetic_visual_state_dict(patch=PATCH, seed=0), True)
+        self.model = CLIP('ViT-B/%d' % cfg['patch'], synthetic_visual_state_dict(patch=cfg['patch'], seed=0), True)
         g = torch.Generator().manual_seed(1234)
         txt = torch.randn(1, 512, generator=g); self.txt = (10. * txt / txt.norm()).cuda()
         self.opt = torch.optim.Adam(self.params, 0.05, betas=(.0, .999))
 
     def step(self, i):
         img_out = self.image_f(None)
-        img_sliced = self.slice_imgs([img_out], S_TOTAL, 224, self.tf, 'uniform', 0.4)[0]
+        img_sliced = self.slice_imgs([img_out], self.S, 224, self.tf, 'uniform', 0.4)[0]
         out_enc = self.model.encode_image(img_sliced)
-        loss = -1. * 1. * self.sim_func(self.txt, out_enc, 'mix')
+        loss = -1. * 1. * self.sim_func(self.txt, out_enc, self.sim)
         self.opt.zero_grad()
         loss.backward()
         self.opt.step()
@@ -231,6 +246,17 @@ def cpu_baseline_port(sample_S, threads=None):
     return {'value': 1.0 / t_full, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
             'sample': 'oracle/restate.py reference_step (fp32, incl. the CLIP weight-gradients the reference also computes), 1280x720 canvas, '
                       '%d of %d crops timed (%.2fs) + 1-crop step (%.2fs), extrapolated linearly in crops to %.2fs/step' % (sample_S, S_TOTAL, tS, t1, t_full)}
+
+
+def run_supplementary(args):
+    """Other BASELINE configs, end to end through the Python entry points only (evidence for profiles/, not the bench line)."""
+    cfg = CONFIGS[args.config]
+    torch.cuda.set_device(0)
+    api = ApiStep(cfg=cfg)
+    t = timed(api.step, args.steps, args.warmup, lambda: None)
+    flops = 2.0 * cfg['S'] * F_VIT[cfg['patch']]
+    print(json.dumps({'config': args.config, 'workload': cfg['note'], 'e2e_steps_per_s': args.steps / t, 'ms_per_step': 1e3 * t / args.steps,
+                      'vit_tflops_of_step': flops / (t / args.steps) / 1e12, 'steps': args.steps, 'warmup': args.warmup}))
 
 
 def run_ours(args):
@@ -400,9 +426,12 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS), help='c2 = the bench line (default); others: supplementary e2e runs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
-    if args.impl == 'reference':
+    if args.impl == 'ours' and args.config != 'c2':
+        run_supplementary(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)
