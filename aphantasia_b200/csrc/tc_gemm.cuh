@@ -30,6 +30,31 @@ struct GemmEpi {
   int unpatch_p = 0;               // >0: out_f32 is [S,3,R,R]; row = s*g*g + gy*g + gx, col = c*p*p + py*p + px
   int unpatch_g = 0;
   int nostore = 0;                 // profiling experiment: epilogue does everything but the global stores
+  // stream-K (set by launch_gemm): CTA groups own contiguous ranges of (tile, k-block) units; a tile split between two
+  // groups is finished by the group holding its first k-blocks, the other parks its fp32 partial in sk_ws
+  int sk = 0;
+  float* sk_ws = nullptr;          // [groups * CG][128][BN] fp32 partial accumulators
+  int* sk_flags = nullptr;         // [groups * CG][8] per-epilogue-warp ready flags (self-resetting)
+};
+
+// Work list of one CTA group: identical in the producer, MMA and epilogue roles.
+struct WorkIter {
+  int sk, G, num_tiles, kblocks, u, u1, tile_rr;
+  __device__ __forceinline__ void init(int sk_, int g, int G_, int num_tiles_, int kblocks_) {
+    sk = sk_; G = G_; num_tiles = num_tiles_; kblocks = kblocks_; tile_rr = g;
+    const long long U = (long long)num_tiles_ * kblocks_;
+    u = (int)((long long)g * U / G_); u1 = (int)((long long)(g + 1) * U / G_);
+  }
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+    if (sk) {
+      if (u >= u1) return false;
+      tile = u / kblocks; kb0 = u - tile * kblocks; kb1 = min(kblocks, kb0 + (u1 - u)); u += kb1 - kb0;
+      return true;
+    }
+    if (tile_rr >= num_tiles) return false;
+    tile = tile_rr; kb0 = 0; kb1 = kblocks; tile_rr += G;
+    return true;
+  }
 };
 
 struct GemmShape { int M, N, K; };
@@ -258,9 +283,11 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ===== TMA producer
       const uint64_t pol_b = l2_policy_evict_last();      // B = weights: shared by all M tiles
       uint32_t it = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      WorkIter wi; wi.init(epi.sk, tile0, tile_step, num_tiles, k_blocks);
+      int tile, kb0, kb1;
+      while (wi.next(tile, kb0, kb1)) {
         const int m_blk = (tile / n_tiles) * CG + (int)rank, n_blk = tile % n_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
@@ -283,12 +310,14 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ===== MMA issuer (the leader CTA issues for the pair when CG = 2)
       constexpr uint32_t idesc = make_idesc_bf16(BN, GEMM_BM * CG);
       uint32_t it = 0, tile_iter = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_iter) {
+      WorkIter wi; wi.init(epi.sk, tile0, tile_step, num_tiles, k_blocks);
+      int tile, kb0, kb1;
+      for (; wi.next(tile, kb0, kb1); ++tile_iter) {
         const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph_ ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -297,15 +326,15 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < GEMM_BK / GEMM_UK; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (>>4) address field
-            if (CG == 2) umma_f16_cg2(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-            else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            if (CG == 2) umma_f16_cg2(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0);
+            else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0);
           }
           if (CG == 2) {
             umma_commit_mc(&empty_bar[s], 0b11);                          // both CTAs' smem stages are free
-            if (kb == k_blocks - 1) umma_commit_mc(&tfull_bar[as], 0b11);   // both CTAs' epilogues may read TMEM
+            if (kb == kb1 - 1) umma_commit_mc(&tfull_bar[as], 0b11);   // both CTAs' epilogues may read TMEM
           } else {
             umma_commit(&empty_bar[s]);                   // smem stage free once these MMAs retire
-            if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);   // accumulator complete
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);   // accumulator (or this group's partial) complete
           }
         }
       }
@@ -318,9 +347,20 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t stage = smem_u32(smem + L::EPI_OFFSET + (warp - 4) * (32 * 128));
     const int c4 = lane & 7, rsub = lane >> 3;
     uint32_t tile_iter = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_iter) {
+    WorkIter wi; wi.init(epi.sk, tile0, tile_step, num_tiles, k_blocks);
+    int tile, kb0, kb1;
+    for (; wi.next(tile, kb0, kb1); ++tile_iter) {
       const int m_blk = (tile / n_tiles) * CG + (int)rank, n_blk = tile % n_tiles;
       const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
+      // stream-K roles of this item: park the partial (tile continues from another group's k-blocks) or fix it up
+      const bool p_store = epi.sk && kb0 > 0, p_fix = epi.sk && kb1 < k_blocks;
+      float* ws_st = epi.sk_ws + ((size_t)(tile0 * CG + (int)rank) * GEMM_BM) * BN;             // slot of this group
+      const float* ws_fx = epi.sk_ws + ((size_t)((tile0 + 1) * CG + (int)rank) * GEMM_BM) * BN;  // slot of the next group
+      if (p_fix) {
+        if (lane == 0) { volatile int* f = epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4); const long long t0 = clock64(); while (*f == 0 && clock64() - t0 < 4000000000LL) { } }   /* bounded (~2 s): a protocol bug must fail a test, not hang the GPU */
+        __threadfence();
+        __syncwarp();
+      }
       mbar_wait(&tfull_bar[as], aph_);
       tc_fence_after();
       const int m_base = m_blk * GEMM_BM + q * 32;
@@ -334,7 +374,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const size_t step = (size_t)4 * shp.N;
         float4 res4[EPI == EPI_BIAS_RESID ? 8 : 1];
         uint2 gin[EPI == EPI_GELUGRAD_BF16 ? 8 : 1];
-        if (EPI == EPI_BIAS_RESID || EPI == EPI_GELUGRAD_BF16) {
+        if ((EPI == EPI_BIAS_RESID || EPI == EPI_GELUGRAD_BF16) && !p_store) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const bool ok = m_base + it * 4 + rsub < shp.M;
@@ -363,6 +403,12 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int m = m_base + rr;
           if (m >= shp.M) break;
           float4 v = lds128(stage + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+          if (p_store || p_fix) {
+            const size_t woff = (size_t)(q * 32 + rr) * BN + c * 32 + 4 * c4;
+            if (p_store) { *reinterpret_cast<float4*>(ws_st + woff) = v; continue; }
+            const float4 w = __ldcg(reinterpret_cast<const float4*>(ws_fx + woff));
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+          }
           if (EPI == EPI_F32) {
             if (epi.nostore) { if (v.x == 1.2345e30f) epi.out_f32[0] = v.y; continue; }
             *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
@@ -395,6 +441,14 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
         __syncwarp();                    // staging tile is reused by this warp's next chunk
+      }
+      if (p_store) {                     // publish this warp's part of the parked partial
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + (tile0 * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 1;
+      } else if (p_fix) {                // consumed: re-arm the flag for the next launch
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 0;
       }
     }
   }

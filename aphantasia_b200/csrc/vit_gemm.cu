@@ -43,9 +43,22 @@ static bool g_prof = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev;
 static std::vector<double> g_prof_flops;
 
+// stream-K scratch (one in-flight GEMM at a time: all launches of this library go to the caller's single stream)
+static float* g_sk_ws = nullptr;
+static int* g_sk_flags = nullptr;
+
+static int sk_prepare() {
+  if (g_sk_ws) return 0;
+  APH_CUDA_OK(cudaMalloc(&g_sk_ws, (size_t)kNumSMs * GEMM_BM * 256 * sizeof(float)));
+  APH_CUDA_OK(cudaMalloc(&g_sk_flags, (size_t)(kNumSMs + 2) * GEMM_EPI_WARPS * sizeof(int)));
+  APH_CUDA_OK(cudaMemset(g_sk_flags, 0, (size_t)(kNumSMs + 2) * GEMM_EPI_WARPS * sizeof(int)));
+  return 0;
+}
+
 template <int BN, int STAGES, int EPI, int CG = 1>
-static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st) {
+static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi_in, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES, CG>;
+  GemmEpi epi = epi_in;
   static bool configured = false;
   if (!configured) {
     APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -56,7 +69,20 @@ static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi
   if (int e = make_tmap_bf16(&mb, B, shp.N, shp.K, BN / CG)) return e;
   const int tiles = ((shp.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * (shp.N / BN);
   const int slots = kNumSMs / CG;
-  const int grid = CG * (tiles < slots ? tiles : slots);
+  const int groups = tiles < slots ? tiles : slots;
+  const int grid = CG * groups;
+  {
+    // stream-K when the static schedule leaves a ragged last round: units = tiles x k-blocks split evenly over the groups
+    static int sk_on = -1;
+    if (sk_on < 0) { const char* e = getenv("APH_GEMM_STREAMK"); sk_on = (e && e[0] == '0') ? 0 : 1; }
+    const int kb = shp.K / GEMM_BK;
+    const long long units = (long long)tiles * kb;
+    const long long cost_static = (long long)((tiles + groups - 1) / groups) * kb, cost_sk = (units + groups - 1) / groups;
+    if (sk_on && tiles > groups && units / groups >= kb && cost_sk + 3 < cost_static) {
+      if (int e = sk_prepare()) return e;
+      epi.sk = 1; epi.sk_ws = g_sk_ws; epi.sk_flags = g_sk_flags;
+    }
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
   if (CG == 2) {
