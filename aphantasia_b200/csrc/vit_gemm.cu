@@ -72,9 +72,12 @@ static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi
   const int groups = tiles < slots ? tiles : slots;
   const int grid = CG * groups;
   {
-    // stream-K when the static schedule leaves a ragged last round: units = tiles x k-blocks split evenly over the groups
+    // stream-K (opt-in, APH_GEMM_STREAMK=1): units = tiles x k-blocks split evenly over the groups, split tiles fixed up through
+    // a parked fp32 partial. Correct (tests pass with it on) but MEASURED SLOWER at the ViT-B shapes (profiles/README.md): with
+    // K = 768 a tile's epilogue costs as much as its main loop, so the extra partial-store / fix-up epilogue per group outweighs
+    // the k-blocks saved by removing the ragged last round (9500x768x768: 31.4 vs 19.1 us; 9500x3072x768: 67.6 vs 47.7 us).
     static int sk_on = -1;
-    if (sk_on < 0) { const char* e = getenv("APH_GEMM_STREAMK"); sk_on = (e && e[0] == '0') ? 0 : 1; }
+    if (sk_on < 0) { const char* e = getenv("APH_GEMM_STREAMK"); sk_on = (e && e[0] == '1') ? 1 : 0; }
     const int kb = shp.K / GEMM_BK;
     const long long units = (long long)tiles * kb;
     const long long cost_static = (long long)((tiles + groups - 1) / groups) * kb, cost_sk = (units + groups - 1) / groups;
