@@ -62,8 +62,8 @@ struct GemmShape { int M, N, K; };
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;       // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int GEMM_UK = 16;       // K per tcgen05.mma (kind::f16)
-constexpr int GEMM_THREADS = 384;      // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue (2 per SM sub-partition)
-constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_EPI_WARPS = 8;      // 2 per SM sub-partition (16 measured identical: the epilogue is bound by the output stores, not by warp latency)
+constexpr int GEMM_THREADS = (4 + GEMM_EPI_WARPS) * 32;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4..: epilogue
 
 // compile-time epilogue kinds (a runtime-flag epilogue was instruction-latency bound: 1 warp per scheduler, long predicated body)
 enum : int {
@@ -343,7 +343,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== epilogue: 8 warps. Warp w reads TMEM lanes 32*(w%4) .. +31 (one accumulator row per lane) and owns the 32-column
     // chunks c = half, half+2, ... (half = (w-4)/4). Each 32x32 fp32 chunk is transposed through a swizzled shared-memory tile
     // so that global traffic is row-contiguous (8 lanes x 16 B = one 128 B line per row); the epilogue kind is compile-time.
-    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int q = warp & 3, half = (warp - 4) >> 2;      // half = column group 0..3 of this warp
     const uint32_t stage = smem_u32(smem + L::EPI_OFFSET + (warp - 4) * (32 * 128));
     const int c4 = lane & 7, rsub = lane >> 3;
     uint32_t tile_iter = 0;
@@ -366,7 +366,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int m_base = m_blk * GEMM_BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = half; c < BN / 32; c += GEMM_EPI_WARPS / 4) {
         // global operands of the fused epilogue are fetched FIRST (8 independent loads in flight per lane): issued inside
         // the store loop they serialise behind the stores (possible aliasing) and the epilogue becomes load-latency bound
         const int col = n_blk * BN + c * 32 + 4 * c4;
@@ -387,7 +387,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_wait_ld();
-        if (c + 2 >= BN / 32) {          // this warp's last read of the accumulator: hand the TMEM stage back
+        if (c + GEMM_EPI_WARPS / 4 >= BN / 32) {          // this warp's last read of the accumulator: hand the TMEM stage back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0)); else mbar_arrive(&tempty_bar[as]); }
