@@ -60,7 +60,66 @@ struct VitImpl {
   bf16* d_qkv = nullptr;         // [M, 3D]
   bf16* d_tok = nullptr;         // [S*g*g, D]
   int last_S = -1;
+  // CUDA-graph cache: the ~90 launches of a forward (or backward) are replayed as one graph when the call repeats with the
+  // same batch size and the same input/output pointers (the optimisation loop does); keyed, small LRU
+  struct GraphEntry { const void* in; const void* out; int S; int flag; cudaGraphExec_t exec; unsigned long long stamp; int nodes; };
+  std::vector<GraphEntry> fwd_graphs, bwd_graphs;
+  std::map<int, int> warm_fwd, warm_bwd;
+  unsigned long long stamp = 0;
 };
+
+bool gemm_profiling_on();      // vit_gemm.cu
+
+static bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("APH_VIT_GRAPH"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1 && !gemm_profiling_on();
+}
+
+// Runs `body` through the graph cache: 1st call with a key runs eagerly (lazy one-time initialisations are not capturable),
+// 2nd call captures + instantiates, later calls replay.
+template <typename Body>
+static int run_cached(std::vector<VitImpl::GraphEntry>& cache, std::map<int, int>& warm, unsigned long long& stamp, const void* in,
+                      const void* out, int S, int flag, cudaStream_t st, Body body) {
+  if (!graphs_enabled()) return body();
+  for (auto& g : cache)
+    if (g.in == in && g.out == out && g.S == S && g.flag == flag) {
+      g.stamp = ++stamp;
+      APH_CUDA_OK(cudaGraphLaunch(g.exec, st));
+      count_launch(g.nodes);           // kernels replayed by the graph
+      return 0;
+    }
+  if (!warm[S]) { warm[S] = 1; return body(); }
+  cudaStreamCaptureStatus cs;
+  APH_CUDA_OK(cudaStreamIsCapturing(st, &cs));
+  if (cs != cudaStreamCaptureStatusNone) return body();          // the caller is capturing already: just contribute the nodes
+  APH_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = body();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc != 0) return rc;
+    return body();                                                 // capture refused: stay eager
+  }
+  size_t nodes = 0;
+  cudaGraphGetNodes(graph, nullptr, &nodes);
+  g_launches.fetch_sub((long long)nodes, std::memory_order_relaxed);   // the capture pass enqueued nothing; the replay below counts
+  cudaGraphExec_t exec = nullptr;
+  if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); cudaGetLastError(); return body(); }
+  cudaGraphDestroy(graph);
+  if (cache.size() >= 4) {                                         // evict the least recently used
+    size_t lru = 0;
+    for (size_t i = 1; i < cache.size(); ++i) if (cache[i].stamp < cache[lru].stamp) lru = i;
+    cudaGraphExecDestroy(cache[lru].exec);
+    cache.erase(cache.begin() + lru);
+  }
+  cache.push_back({in, out, S, flag, exec, ++stamp, (int)nodes});
+  APH_CUDA_OK(cudaGraphLaunch(exec, st));
+  count_launch((int)nodes);
+  return 0;
+}
 
 template <typename Tp>
 static int dev_alloc(VitImpl* v, Tp** p, size_t count) {
@@ -167,6 +226,8 @@ extern "C" int aph_vit_create(aph_vit** out, const aph_vit_config* cfg) {
 extern "C" int aph_vit_destroy(aph_vit* vit) {
   if (!vit) return 0;
   VitImpl* v = reinterpret_cast<VitImpl*>(vit);
+  for (auto& g : v->fwd_graphs) cudaGraphExecDestroy(g.exec);
+  for (auto& g : v->bwd_graphs) cudaGraphExecDestroy(g.exec);
   for (void* p : v->allocs) cudaFree(p);
   delete v;
   return 0;
@@ -239,6 +300,7 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
   APH_REQUIRE(v->finalized, "aph_vit_fwd: weights not finalized");
   APH_REQUIRE(S > 0 && S <= v->cfg.max_batch, "aph_vit_fwd: S=%d outside (0, max_batch=%d]", S, v->cfg.max_batch);
   cudaStream_t st = (cudaStream_t)stream;
+  const int rc = run_cached(v->fwd_graphs, v->warm_fwd, v->stamp, images, emb, S, save_for_bwd, st, [&]() -> int {
   const int D = v->D, T = v->T, g = v->g, Ly = v->cfg.layers, O = v->cfg.out_dim, H = v->cfg.heads;
   const int M = S * T, Mp = S * g * g;
   const size_t Mmax = (size_t)v->cfg.max_batch * T;
@@ -282,6 +344,9 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
     GemmEpi ep; ep.out_f32 = emb;
     if ((e = launch_gemm(v->cls_ln, v->w_out, GemmShape{S, O, D}, ep, st))) return e;
   }
+  return 0;
+  });
+  if (rc) return rc;
   v->last_S = save_for_bwd ? S : -1;
   return 0;
 }
@@ -291,6 +356,7 @@ extern "C" int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* gr
   VitImpl* v = reinterpret_cast<VitImpl*>(vit);
   APH_REQUIRE(v->last_S == S, "aph_vit_bwd: no saved forward for S=%d (last saved S=%d)", S, v->last_S);
   cudaStream_t st = (cudaStream_t)stream;
+  return run_cached(v->bwd_graphs, v->warm_bwd, v->stamp, grad_emb, grad_images, S, 0, st, [&]() -> int {
   const int D = v->D, T = v->T, g = v->g, Ly = v->cfg.layers, O = v->cfg.out_dim, H = v->cfg.heads;
   const int M = S * T, Mp = S * g * g;
   const size_t Mmax = (size_t)v->cfg.max_batch * T;
@@ -336,4 +402,5 @@ extern "C" int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* gr
   { GemmEpi ep; ep.out_f32 = grad_images; ep.unpatch_p = v->cfg.patch; ep.unpatch_g = g;
     if ((e = launch_gemm(v->d_tok, v->w_conv_t, GemmShape{Mp, v->Kp, D}, ep, st))) return e; }
   return 0;
+  });
 }

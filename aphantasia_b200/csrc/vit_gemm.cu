@@ -40,6 +40,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int K, int box_
 
 // ---- optional per-launch event timing (bench.py's roofline: the GEMM kernel's real time inside a step)
 static bool g_prof = false;
+bool gemm_profiling_on() { return g_prof; }
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev;
 static std::vector<double> g_prof_flops;
 
