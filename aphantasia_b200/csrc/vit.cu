@@ -80,7 +80,7 @@ static bool graphs_enabled() {
 // 2nd call captures + instantiates, later calls replay.
 template <typename Body>
 static int run_cached(std::vector<VitImpl::GraphEntry>& cache, std::map<int, int>& warm, unsigned long long& stamp, const void* in,
-                      const void* out, int S, int flag, cudaStream_t st, Body body) {
+                      const void* out, int S, int flag, cudaStream_t& st, Body body) {
   if (!graphs_enabled()) return body();
   for (auto& g : cache)
     if (g.in == in && g.out == out && g.S == S && g.flag == flag) {
@@ -90,13 +90,17 @@ static int run_cached(std::vector<VitImpl::GraphEntry>& cache, std::map<int, int
       return 0;
     }
   if (!warm[S]) { warm[S] = 1; return body(); }
-  cudaStreamCaptureStatus cs;
-  APH_CUDA_OK(cudaStreamIsCapturing(st, &cs));
-  if (cs != cudaStreamCaptureStatusNone) return body();          // the caller is capturing already: just contribute the nodes
-  APH_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  // The caller's stream is often the legacy default stream (torch's default), which cannot be captured: record the launch
+  // sequence on a private stream (`st` is what the body launches on -- capture enqueues nothing), replay on the caller's.
+  static cudaStream_t cap = nullptr;
+  if (!cap) APH_CUDA_OK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  cudaStream_t user = st;
+  st = cap;
+  if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); st = user; return body(); }
   const int rc = body();
   cudaGraph_t graph = nullptr;
-  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+  st = user;
   if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
     if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
