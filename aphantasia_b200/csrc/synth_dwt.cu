@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(256) k_dwt_level_bwd(const float* __restrict__
 }
 
 // g_x = (c/sigma) (g_img - (x - mu) * dot / ((N-1) sigma^2))      (adjoint of img = x * c / std(x))
-__global__ void __launch_bounds__(256) k_norm_bwd(const float* __restrict__ gimg, const float* __restrict__ x_raw,
-                                                  const double* __restrict__ stats, float* __restrict__ gx, size_t n, float contrast) {
+__global__ void __launch_bounds__(256) k_norm_bwd(const float* gimg, const float* __restrict__ x_raw,
+                                                  const double* __restrict__ stats, float* gx, size_t n, float contrast) {   // gimg may alias gx
   const double Nn = (double)n;
   const double mu = stats[0] / Nn;
   const double var = (stats[1] - stats[0] * stats[0] / Nn) / (Nn - 1.0);
@@ -120,6 +120,23 @@ __global__ void __launch_bounds__(256) k_norm_bwd(const float* __restrict__ gimg
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     gx[i] = c_sig * (gimg[i] - (x_raw[i] - muf) * kk);
 }
+
+// sum x, sum x^2 over n floats -> stats[0], stats[1] (fp64 atomics)
+__global__ void __launch_bounds__(256) k_stats(const float* __restrict__ x, size_t n, double* __restrict__ stats) {
+  double s1 = 0., s2 = 0.;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { const float v = x[i]; s1 += v; s2 += (double)v * v; }
+  s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+  __shared__ double red[2][8];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][wid] = s1; red[1][wid] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0., t2 = 0.;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { t1 += red[0][i]; t2 += red[1][i]; }
+    atomicAdd(&stats[0], t1); atomicAdd(&stats[1], t2);
+  }
+}
+__global__ void k_fix_stats(double* stats, double n, double sigma) { stats[0] = 0.; stats[1] = sigma * sigma * (n - 1.0); stats[2] = 0.; }
 
 static inline int grid_for(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 16); }
 
@@ -216,5 +233,35 @@ extern "C" int aph_synth_dwt_bwd(aph_dwt_plan* plan, const float* grad_out, cons
     k_dwt_level_bwd<<<grid_for(n), 256, 0, st>>>(dout, p->oh[i], p->ow[i], dll, llh, llw, grad_Ys[i + 1], scales_host[i], p->lh[i], p->lw[i], p->f);
     APH_LAUNCH_OK();
   }
+  return 0;
+}
+
+// Direct RGB parameterisation (pixel_image, /root/reference/aphantasia/image.py:98-119): img = x * contrast / std(x), or
+// x * contrast / 3.3 with fixcontrast; fused with to_valid_rgb like the spectral generators. x, out, grad_x: [3,H,W].
+extern "C" int aph_pixel_fwd(const float* x, int64_t hw, float contrast, int fixcontrast, const float* colmat_host, int apply_sigmoid,
+                             double* stats, float* out, void* stream) {
+  APH_REQUIRE(x && stats && out && hw > 0, "aph_pixel_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  APH_CUDA_OK(cudaMemsetAsync(stats, 0, 4 * sizeof(double), st));
+  if (fixcontrast) k_fix_stats<<<1, 1, 0, st>>>(stats, 3.0 * (double)hw, 3.3);       // sigma := 3.3 (image.py:115)
+  else k_stats<<<grid_for(3 * (size_t)hw), 256, 0, st>>>(x, 3 * (size_t)hw, stats);
+  APH_LAUNCH_OK();
+  k_finish<<<grid_for((size_t)hw), 256, 0, st>>>(x, stats, out, (size_t)hw, contrast, make_colmat(colmat_host), apply_sigmoid);
+  APH_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int aph_pixel_bwd(const float* grad_out, const float* out, const float* x, double* stats, int64_t hw, float contrast,
+                             int fixcontrast, const float* colmat_host, int apply_sigmoid, float* grad_x, void* stream) {
+  APH_REQUIRE(grad_out && x && stats && grad_x && hw > 0, "aph_pixel_bwd: bad arguments");
+  APH_REQUIRE(!apply_sigmoid || out, "aph_pixel_bwd: sigmoid backward needs the saved output");
+  cudaStream_t st = (cudaStream_t)stream;
+  APH_CUDA_OK(cudaMemsetAsync(stats + 2, 0, sizeof(double), st));
+  // g_img lands in grad_x, then is rewritten in place by the normalisation adjoint (with fixcontrast the std term vanishes)
+  k_finish_bwd<<<grid_for((size_t)hw), 256, 0, st>>>(grad_out, out, fixcontrast ? nullptr : x, grad_x, stats, (size_t)hw,
+                                                     make_colmat(colmat_host), apply_sigmoid);
+  APH_LAUNCH_OK();
+  k_norm_bwd<<<grid_for(3 * (size_t)hw), 256, 0, st>>>(grad_x, x, stats, grad_x, 3 * (size_t)hw, contrast);
+  APH_LAUNCH_OK();
   return 0;
 }

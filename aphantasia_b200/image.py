@@ -129,6 +129,63 @@ def fft_image(shape, sd=0.01, decay_power=1.0, resume=None):
     return [spectrum_real_imag_t], FFTImage(spectrum_real_imag_t, h, w, decay_power), size
 
 
+class _SynthPixel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, contrast, fixcontrast, colmat, sigmoid):
+        require_cuda(x, 'pixel parameters')
+        xi = x.detach().contiguous().float()
+        assert xi.shape[0] == 1 and xi.shape[1] == 3, 'pixel_image expects [1,3,H,W]'
+        hw = xi.shape[2] * xi.shape[3]
+        out = torch.empty_like(xi)
+        stats = torch.empty(4, device=xi.device, dtype=torch.float64)
+        check(lib().aph_pixel_fwd(xi.data_ptr(), hw, float(contrast), int(bool(fixcontrast)), colmat, int(sigmoid), stats.data_ptr(),
+                                  out.data_ptr(), stream_ptr()), 'aph_pixel_fwd')
+        ctx.args = (hw, float(contrast), int(bool(fixcontrast)), colmat, int(sigmoid))
+        ctx.save_for_backward(xi, stats, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xi, stats, out = ctx.saved_tensors
+        hw, contrast, fix, colmat, sig = ctx.args
+        g = g.contiguous().float()
+        gx = torch.empty_like(xi)
+        check(lib().aph_pixel_bwd(g.data_ptr(), out.data_ptr(), xi.data_ptr(), stats.data_ptr(), hw, contrast, fix, colmat, sig, gx.data_ptr(),
+                                  stream_ptr()), 'aph_pixel_bwd')
+        return gx, None, None, None, None
+
+
+class PixelImage:
+    """The `image_f` closure of pixel_image (image.py:112-118) as a callable object (fusable by to_valid_rgb)."""
+
+    def __init__(self, image_t):
+        self.image_t = image_t
+
+    def fused(self, shift, contrast, colmat, sigmoid, fixcontrast=False):
+        return _SynthPixel.apply(self.image_t, contrast, fixcontrast, colmat, sigmoid)
+
+    def __call__(self, shift=None, contrast=1., fixcontrast=False):
+        return self.fused(shift, contrast, None, False, fixcontrast)
+
+
+def pixel_image(shape, resume=None, sd=1., *noargs, **nokwargs):
+    """Drop-in for image.py:98-119 (illustrip's default generator): returns ([image_t], image_f, size)."""
+    _dist.init()
+    size = None
+    if resume is None:
+        image_t = torch.randn(*shape) * sd
+    elif isinstance(resume, str):
+        raise NotImplementedError('aphantasia_b200: pixel_image resume from an image file (un_rgb) is init-time, out of the hot path')
+    else:
+        if isinstance(resume, list): resume = resume[0]
+        image_t = resume
+    image_t = image_t.cuda()
+    if resume is None and _dist.world() > 1:
+        torch.distributed.broadcast(image_t, 0)
+    image_t = image_t.requires_grad_(True)
+    return [image_t], PixelImage(image_t), size
+
+
 class _ValidRGB(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, colmat):
@@ -157,9 +214,11 @@ def to_valid_rgb(image_f, colors=1., decorrelate=True):
     colmat = _color_matrix_host(colors) if decorrelate else None
 
     def inner(*args, **kwargs):
-        if isinstance(image_f, (FFTImage, DWTImage)):
+        if isinstance(image_f, (FFTImage, DWTImage, PixelImage)):
             shift = args[0] if len(args) > 0 else kwargs.get('shift', None)
             contrast = args[1] if len(args) > 1 else kwargs.get('contrast', 1.)
+            if isinstance(image_f, PixelImage):
+                return image_f.fused(shift, contrast, colmat, True, args[2] if len(args) > 2 else kwargs.get('fixcontrast', False))
             return image_f.fused(shift, contrast, colmat, True)
         return _ValidRGB.apply(image_f(*args, **kwargs), colmat)
     return inner

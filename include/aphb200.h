@@ -94,6 +94,13 @@ int aph_synth_dwt_bwd(aph_dwt_plan* plan, const float* grad_out, const float* ou
                       double* stats, const float* scales_host, float contrast, const float* colmat_host,
                       int apply_sigmoid, float* const* grad_Ys, void* stream);
 
+/* Direct RGB parameterisation: pixel_image.inner (aphantasia/image.py:112-118): img = x*contrast/std(x) (or /3.3 with
+ * fixcontrast), fused with to_valid_rgb. x / out / grad_x are [3,H,W]; stats as above.                             */
+int aph_pixel_fwd(const float* x, int64_t hw, float contrast, int fixcontrast, const float* colmat_host,
+                  int apply_sigmoid, double* stats, float* out, void* stream);
+int aph_pixel_bwd(const float* grad_out, const float* out, const float* x, double* stats, int64_t hw, float contrast,
+                  int fixcontrast, const float* colmat_host, int apply_sigmoid, float* grad_x, void* stream);
+
 /* Stand-alone to_valid_rgb for a foreign image_f (aphantasia/image.py:21-28): img [3,H,W] -> out.  */
 int aph_valid_rgb_fwd(const float* img, int64_t hw, const float* colmat_host, float* out, void* stream);
 int aph_valid_rgb_bwd(const float* grad_out, const float* out, int64_t hw, const float* colmat_host,

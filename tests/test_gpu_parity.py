@@ -347,3 +347,19 @@ def test_sampler_config5_shape_properties(L):
     lhs = (c.grad * b).sum().item()
     rhs = ((un(run(b)) * cot) / std).sum().item()    # <cot, L b> with L the linear part of the sampler
     assert abs(lhs - rhs) < 1e-3 * abs(rhs)
+
+
+@pytest.mark.parametrize('fix', [False, True])
+def test_pixel_image_vs_oracle(L, fix):
+    """Next-row generator: pixel_image + to_valid_rgb vs the restatement of image.py:98-119."""
+    from aphantasia_b200.image import pixel_image, to_valid_rgb
+    _seed(12)
+    params, image_f, _ = pixel_image([1, 3, 90, 130], None, 1.)
+    rgb = to_valid_rgb(image_f, colors=2.)(None, 1.1, fix)
+    cot = torch.randn(rgb.shape)
+    (rgb * cot.cuda()).sum().backward()
+    xo = params[0].detach().cpu().clone().requires_grad_(True)
+    ref = R.valid_rgb(R.synth_pixel(xo, 1.1, fix), R.color_matrix(2.))
+    (ref * cot).sum().backward()
+    assert _rel(rgb, ref) < 1e-6 and _rel(params[0].grad, xo.grad) < 1e-5
+    assert _rel(image_f(contrast=0.7), R.synth_pixel(xo.detach(), 0.7)) < 1e-6
