@@ -66,6 +66,7 @@ struct VitImpl {
   std::vector<GraphEntry> fwd_graphs, bwd_graphs;
   std::map<int, int> warm_fwd, warm_bwd;
   unsigned long long stamp = 0;
+  int graph_misses = 0;          // captures in a row that were never replayed (e.g. the caller re-allocates its tensors every step)
 };
 
 bool gemm_profiling_on();      // vit_gemm.cu
@@ -79,12 +80,15 @@ static bool graphs_enabled() {
 // Runs `body` through the graph cache: 1st call with a key runs eagerly (lazy one-time initialisations are not capturable),
 // 2nd call captures + instantiates, later calls replay.
 template <typename Body>
-static int run_cached(std::vector<VitImpl::GraphEntry>& cache, std::map<int, int>& warm, unsigned long long& stamp, const void* in,
-                      const void* out, int S, int flag, cudaStream_t& st, Body body) {
-  if (!graphs_enabled()) return body();
+static int run_cached(std::vector<VitImpl::GraphEntry>& cache, std::map<int, int>& warm, unsigned long long& stamp, int& misses,
+                      const void* in, const void* out, int S, int flag, cudaStream_t& st, Body body) {
+  // a caller whose buffers move every step (clip_fft.py calls torch.cuda.empty_cache() per step) would re-capture forever:
+  // after 6 never-replayed captures in a row the handle stays eager
+  if (!graphs_enabled() || misses > 6) return body();
   for (auto& g : cache)
     if (g.in == in && g.out == out && g.S == S && g.flag == flag) {
       g.stamp = ++stamp;
+      misses = 0;
       APH_CUDA_OK(cudaGraphLaunch(g.exec, st));
       count_launch(g.nodes);           // kernels replayed by the graph
       return 0;
@@ -119,6 +123,7 @@ static int run_cached(std::vector<VitImpl::GraphEntry>& cache, std::map<int, int
     cudaGraphExecDestroy(cache[lru].exec);
     cache.erase(cache.begin() + lru);
   }
+  ++misses;
   cache.push_back({in, out, S, flag, exec, ++stamp, (int)nodes});
   APH_CUDA_OK(cudaGraphLaunch(exec, st));
   count_launch((int)nodes);
@@ -304,7 +309,7 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
   APH_REQUIRE(v->finalized, "aph_vit_fwd: weights not finalized");
   APH_REQUIRE(S > 0 && S <= v->cfg.max_batch, "aph_vit_fwd: S=%d outside (0, max_batch=%d]", S, v->cfg.max_batch);
   cudaStream_t st = (cudaStream_t)stream;
-  const int rc = run_cached(v->fwd_graphs, v->warm_fwd, v->stamp, images, emb, S, save_for_bwd, st, [&]() -> int {
+  const int rc = run_cached(v->fwd_graphs, v->warm_fwd, v->stamp, v->graph_misses, images, emb, S, save_for_bwd, st, [&]() -> int {
   const int D = v->D, T = v->T, g = v->g, Ly = v->cfg.layers, O = v->cfg.out_dim, H = v->cfg.heads;
   const int M = S * T, Mp = S * g * g;
   const size_t Mmax = (size_t)v->cfg.max_batch * T;
@@ -360,7 +365,7 @@ extern "C" int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* gr
   VitImpl* v = reinterpret_cast<VitImpl*>(vit);
   APH_REQUIRE(v->last_S == S, "aph_vit_bwd: no saved forward for S=%d (last saved S=%d)", S, v->last_S);
   cudaStream_t st = (cudaStream_t)stream;
-  return run_cached(v->bwd_graphs, v->warm_bwd, v->stamp, grad_emb, grad_images, S, 0, st, [&]() -> int {
+  return run_cached(v->bwd_graphs, v->warm_bwd, v->stamp, v->graph_misses, grad_emb, grad_images, S, 0, st, [&]() -> int {
   const int D = v->D, T = v->T, g = v->g, Ly = v->cfg.layers, O = v->cfg.out_dim, H = v->cfg.heads;
   const int M = S * T, Mp = S * g * g;
   const size_t Mmax = (size_t)v->cfg.max_batch * T;
