@@ -250,6 +250,7 @@ template <int BN, int STAGES, int EPI, int CG = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape shp, GemmEpi epi) {
   using L = GemmSmem<BN, STAGES, CG>;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -277,6 +278,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // everything above overlapped the previous kernel's tail; operands are read from here on
 
   if (warp == 0) {
     if (lane == 0) {

@@ -317,12 +317,12 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
   // patch embedding
   {
     const size_t n8 = (size_t)Mp * v->Kp / 8;
-    k_patchify<<<(int)std::min<size_t>((n8 + 255) / 256, (size_t)kNumSMs * 16), 256, 0, st>>>(images, v->patches, S, v->cfg.patch, g);
+    APH_CUDA_OK(launch_k(k_patchify, dim3((unsigned)std::min<size_t>((n8 + 255) / 256, (size_t)kNumSMs * 16)), dim3(256), (size_t)0, st, 1, images, v->patches, S, v->cfg.patch, g));
     APH_LAUNCH_OK();
     GemmEpi ep; ep.out_f32 = v->tok;
     if ((e = launch_gemm(v->patches, v->w_conv, GemmShape{Mp, D, v->Kp}, ep, st))) return e;
-    NCH_DISPATCH(D, k_embed_lnpre<NCH><<<rows_grid(M), 256, 0, st>>>(v->tok, v->cls, v->pos, v->lnpre_w, v->lnpre_b, v->e, v->xs[0],
-                                                                      v->st_mean, v->st_rstd, S, T, D));
+    NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_embed_lnpre<NCH>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, v->tok, v->cls, v->pos, v->lnpre_w, v->lnpre_b, v->e, v->xs[0],
+                                                                      v->st_mean, v->st_rstd, S, T, D)));
     APH_LAUNCH_OK();
   }
   for (int l = 0; l < Ly; ++l) {
@@ -330,7 +330,7 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
     float* x_in = v->xs[2 * l]; float* x_mid = v->xs[2 * l + 1]; float* x_out = v->xs[2 * l + 2];
     float* mean1 = v->st_mean + (size_t)(1 + 2 * l) * Mmax; float* rstd1 = v->st_rstd + (size_t)(1 + 2 * l) * Mmax;
     float* mean2 = mean1 + Mmax; float* rstd2 = rstd1 + Mmax;
-    NCH_DISPATCH(D, k_ln_fwd<NCH><<<rows_grid(M), 256, 0, st>>>(x_in, (size_t)D, w.ln1_w, w.ln1_b, v->ln_out, mean1, rstd1, M, D));
+    NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_fwd<NCH>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, x_in, (size_t)D, w.ln1_w, w.ln1_b, v->ln_out, mean1, rstd1, M, D)));
     APH_LAUNCH_OK();
     { GemmEpi ep; ep.bias = w.b_qkv; ep.out_bf16 = v->qkv[l];
       if ((e = launch_gemm(v->ln_out, w.w_qkv, GemmShape{M, 3 * D, D}, ep, st))) return e; }
@@ -338,7 +338,7 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
     else if ((e = attn_dispatch(true, v->qkv[l], nullptr, v->attn_out, S, T, D, H, st))) return e;
     { GemmEpi ep; ep.bias = w.b_o; ep.resid = x_in; ep.out_f32 = x_mid;
       if ((e = launch_gemm(v->attn_out, w.w_o, GemmShape{M, D, D}, ep, st))) return e; }
-    NCH_DISPATCH(D, k_ln_fwd<NCH><<<rows_grid(M), 256, 0, st>>>(x_mid, (size_t)D, w.ln2_w, w.ln2_b, v->ln_out, mean2, rstd2, M, D));
+    NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_fwd<NCH>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, x_mid, (size_t)D, w.ln2_w, w.ln2_b, v->ln_out, mean2, rstd2, M, D)));
     APH_LAUNCH_OK();
     { GemmEpi ep; ep.bias = w.b_fc; ep.out_pre = v->h_pre[l]; ep.act = 1; ep.out_bf16 = v->h_act;
       if ((e = launch_gemm(v->ln_out, w.w_fc, GemmShape{M, 4 * D, D}, ep, st))) return e; }
@@ -347,8 +347,8 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
   }
   {
     float* meanp = v->st_mean + (size_t)(2 * Ly + 1) * Mmax; float* rstdp = v->st_rstd + (size_t)(2 * Ly + 1) * Mmax;
-    NCH_DISPATCH(D, k_ln_fwd<NCH><<<rows_grid(S), 256, 0, st>>>(v->xs[2 * Ly], (size_t)T * D, v->lnpost_w, v->lnpost_b, v->cls_ln,
-                                                                 meanp, rstdp, S, D));
+    NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_fwd<NCH>, dim3(rows_grid(S)), dim3(256), (size_t)0, st, 1, v->xs[2 * Ly], (size_t)T * D, v->lnpost_w, v->lnpost_b, v->cls_ln,
+                                                                 meanp, rstdp, S, D)));
     APH_LAUNCH_OK();
     GemmEpi ep; ep.out_f32 = emb;
     if ((e = launch_gemm(v->cls_ln, v->w_out, GemmShape{S, O, D}, ep, st))) return e;
@@ -372,15 +372,15 @@ extern "C" int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* gr
   int e;
   {
     const size_t n = (size_t)S * O;
-    k_f32_to_bf16<<<(int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8), 256, 0, st>>>(grad_emb, v->d_emb, n);
+    APH_CUDA_OK(launch_k(k_f32_to_bf16, dim3((int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8)), dim3(256), (size_t)0, st, 1, grad_emb, v->d_emb, n));
     APH_LAUNCH_OK();
     GemmEpi ep; ep.out_f32 = v->d_cls;
     if ((e = launch_gemm(v->d_emb, v->w_out_t, GemmShape{S, D, O}, ep, st))) return e;
     APH_CUDA_OK(cudaMemsetAsync(v->dx, 0, (size_t)M * D * sizeof(float), st));
     APH_CUDA_OK(cudaMemsetAsync(v->dx_bf, 0, (size_t)M * D * sizeof(bf16), st));
     float* meanp = v->st_mean + (size_t)(2 * Ly + 1) * Mmax; float* rstdp = v->st_rstd + (size_t)(2 * Ly + 1) * Mmax;
-    NCH_DISPATCH(D, k_ln_bwd<NCH><<<rows_grid(S), 256, 0, st>>>(v->d_cls, v->xs[2 * Ly], meanp, rstdp, v->lnpost_w, v->dx, v->dx_bf,
-                                                                 S, T, D, 1, 0));
+    NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_bwd<NCH>, dim3(rows_grid(S)), dim3(256), (size_t)0, st, 1, v->d_cls, v->xs[2 * Ly], meanp, rstdp, v->lnpost_w, v->dx, v->dx_bf,
+                                                                 S, T, D, 1, 0)));
     APH_LAUNCH_OK();
   }
   for (int l = Ly - 1; l >= 0; --l) {
@@ -393,7 +393,7 @@ extern "C" int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* gr
       if ((e = launch_gemm(v->dx_bf, w.w_proj_t, GemmShape{M, 4 * D, D}, ep, st))) return e; }
     { GemmEpi ep; ep.out_f32 = v->d_ln;
       if ((e = launch_gemm(v->dh, w.w_fc_t, GemmShape{M, D, 4 * D}, ep, st))) return e; }
-    NCH_DISPATCH(D, k_ln_bwd<NCH><<<rows_grid(M), 256, 0, st>>>(v->d_ln, x_mid, mean2, rstd2, w.ln2_w, v->dx, v->dx_bf, M, T, D, 0, 1));
+    NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_bwd<NCH>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, v->d_ln, x_mid, mean2, rstd2, w.ln2_w, v->dx, v->dx_bf, M, T, D, 0, 1)));
     APH_LAUNCH_OK();
     // attention branch: d_attn = dx . W_o; (dq,dk,dv) = attn'(...); d_ln1 = d_qkv . W_qkv
     { GemmEpi ep; ep.out_bf16 = v->d_attn;
@@ -402,11 +402,11 @@ extern "C" int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* gr
     else if ((e = attn_dispatch(false, v->qkv[l], v->d_attn, v->d_qkv, S, T, D, H, st))) return e;
     { GemmEpi ep; ep.out_f32 = v->d_ln;
       if ((e = launch_gemm(v->d_qkv, w.w_qkv_t, GemmShape{M, D, 3 * D}, ep, st))) return e; }
-    NCH_DISPATCH(D, k_ln_bwd<NCH><<<rows_grid(M), 256, 0, st>>>(v->d_ln, x_in, mean1, rstd1, w.ln1_w, v->dx, v->dx_bf, M, T, D, 0, 1));
+    NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_bwd<NCH>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, v->d_ln, x_in, mean1, rstd1, w.ln1_w, v->dx, v->dx_bf, M, T, D, 0, 1)));
     APH_LAUNCH_OK();
   }
   // ln_pre backward (cls rows dropped) and patch-embed data gradient scattered back to NCHW
-  NCH_DISPATCH(D, k_ln_bwd<NCH><<<rows_grid(M), 256, 0, st>>>(v->dx, v->e, v->st_mean, v->st_rstd, v->lnpre_w, nullptr, v->d_tok, M, T, D, 2, 0));
+  NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_bwd<NCH>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, v->dx, v->e, v->st_mean, v->st_rstd, v->lnpre_w, nullptr, v->d_tok, M, T, D, 2, 0)));
   APH_LAUNCH_OK();
   { GemmEpi ep; ep.out_f32 = grad_images; ep.unpatch_p = v->cfg.patch; ep.unpatch_g = g;
     if ((e = launch_gemm(v->d_tok, v->w_conv_t, GemmShape{Mp, v->Kp, D}, ep, st))) return e; }

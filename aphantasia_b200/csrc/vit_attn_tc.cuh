@@ -82,6 +82,7 @@ __device__ __forceinline__ void av_step(float (&acc)[8][4], const uint32_t (&a)[
 // ---------------------------------------------------------------------------------------------
 template <int NW, int NT2>
 __global__ void __launch_bounds__(NW * 32) k_attn_fwd_tc(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int D, int heads) {
+  pdl_trigger(); pdl_wait();
   extern __shared__ __align__(128) uint8_t sm[];
   constexpr int TK = NT2 * 16, QB = NW * 16;
   uint8_t* Ks = sm; uint8_t* Vs = Ks + TK * 128; uint8_t* Qs = Vs + TK * 128;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(NW * 32) k_attn_fwd_tc(const bf16* __restrict_
 template <int NW, int NT2>
 __global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1) k_attn_bwd_tc(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
                                                          int T, int D, int heads) {
+  pdl_trigger(); pdl_wait();
   extern __shared__ __align__(128) uint8_t sm[];
   constexpr int TK = NT2 * 16, QB = NW * 16, KT = (NT2 + NW - 1) / NW, PB = ((TK + 63) / 64) * 128;
   uint8_t* Ks = sm; uint8_t* Vs = Ks + TK * 128; uint8_t* Qs = Vs + TK * 128; uint8_t* Gs = Qs + QB * 128;
@@ -370,6 +372,7 @@ __device__ __forceinline__ void load_tile64_async(uint32_t tile, const bf16* __r
 
 template <int NT2>
 __global__ void __launch_bounds__(128) k_attn_fwd_tc1(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int D, int heads, int items) {
+  pdl_trigger(); pdl_wait();
   extern __shared__ __align__(128) uint8_t sm[];
   constexpr int TK = NT2 * 16, QB = 64, BUF = (2 * TK + QB) * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -442,6 +445,7 @@ __global__ void __launch_bounds__(128) k_attn_fwd_tc1(const bf16* __restrict__ q
 template <int NT2>
 __global__ void __launch_bounds__(128, 2) k_attn_bwd_tc1(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
                                                          int T, int D, int heads, int items) {
+  pdl_trigger(); pdl_wait();
   extern __shared__ __align__(128) uint8_t sm[];
   constexpr int TK = NT2 * 16, QB = 64, PB = 128, BUF = (2 * TK + 2 * QB) * 128;
   uint8_t* Ps = sm + 2 * BUF; uint8_t* Ds = Ps + QB * PB;
@@ -575,11 +579,11 @@ static int attn_launch1(bool fwd, const bf16* qkv, const bf16* dout, bf16* out_o
   if (fwd) {
     const int per_sm = (int)(220 * 1024 / smem_f) < 6 ? (int)(220 * 1024 / smem_f) : 6;
     const int grid = items < kNumSMs * per_sm ? items : kNumSMs * per_sm;
-    k_attn_fwd_tc1<NT2><<<grid, 128, smem_f, st>>>(qkv, out_or_dqkv, T, D, heads, items);
+    APH_CUDA_OK(launch_k(k_attn_fwd_tc1<NT2>, dim3(grid), dim3(128), smem_f, st, 1, qkv, out_or_dqkv, T, D, heads, items));
   } else {
     const int per_sm = (int)(220 * 1024 / smem_b) < 3 ? (int)(220 * 1024 / smem_b) : 3;
     const int grid = items < kNumSMs * per_sm ? items : kNumSMs * per_sm;
-    k_attn_bwd_tc1<NT2><<<grid, 128, smem_b, st>>>(qkv, dout, out_or_dqkv, T, D, heads, items);
+    APH_CUDA_OK(launch_k(k_attn_bwd_tc1<NT2>, dim3(grid), dim3(128), smem_b, st, 1, qkv, dout, out_or_dqkv, T, D, heads, items));
   }
   APH_LAUNCH_OK();
   return 0;
@@ -601,8 +605,8 @@ static int attn_launch(bool fwd, const bf16* qkv, const bf16* dout, bf16* out_or
     APH_CUDA_OK(cudaFuncSetAttribute(k_attn_bwd_tc<NW, NT2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     cfg = true;
   }
-  if (fwd) k_attn_fwd_tc<NW, NT2><<<S * heads, NW * 32, attn_tc_fwd_smem<NW, NT2>(), st>>>(qkv, out_or_dqkv, T, D, heads);
-  else k_attn_bwd_tc<NW, NT2><<<S * heads, NW * 32, attn_tc_bwd_smem<NW, NT2>(), st>>>(qkv, dout, out_or_dqkv, T, D, heads);
+  if (fwd) APH_CUDA_OK(launch_k(k_attn_fwd_tc<NW, NT2>, dim3(S * heads), dim3(NW * 32), attn_tc_fwd_smem<NW, NT2>(), st, 1, qkv, out_or_dqkv, T, D, heads));
+  else APH_CUDA_OK(launch_k(k_attn_bwd_tc<NW, NT2>, dim3(S * heads), dim3(NW * 32), attn_tc_bwd_smem<NW, NT2>(), st, 1, qkv, dout, out_or_dqkv, T, D, heads));
   APH_LAUNCH_OK();
   return 0;
 }

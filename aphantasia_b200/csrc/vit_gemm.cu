@@ -89,17 +89,7 @@ static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
-  if (CG == 2) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    APH_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_bf16_tn<BN, STAGES, EPI, CG>, ma, mb, shp, epi));
-  } else {
-    k_gemm_bf16_tn<BN, STAGES, EPI, CG><<<grid, GEMM_THREADS, L::TOTAL, st>>>(ma, mb, shp, epi);
-  }
+  APH_CUDA_OK(launch_k(k_gemm_bf16_tn<BN, STAGES, EPI, CG>, dim3(grid), dim3(GEMM_THREADS), (size_t)L::TOTAL, st, CG, ma, mb, shp, epi));
   APH_LAUNCH_OK();
   if (g_prof) { cudaEventRecord(e1, st); g_prof_ev.emplace_back(e0, e1); g_prof_flops.push_back(2.0 * shp.M * shp.N * shp.K); }
   return 0;

@@ -12,6 +12,7 @@ namespace aph {
 // ---------------------------------------------------------------------------------------------
 // images fp32 [S,3,R,R] -> patches bf16 [S*g*g, 3*p*p], col = c*p*p + py*p + px  (conv1 weight layout)
 __global__ void __launch_bounds__(256) k_patchify(const float* __restrict__ img, bf16* __restrict__ out, int S, int p, int g) {
+  pdl_trigger(); pdl_wait();
   const int R = p * g, Kp = 3 * p * p;
   const size_t total = (size_t)S * g * g * Kp / 8;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(256) k_patchify(const float* __restrict__ img,
 }
 
 __global__ void __launch_bounds__(256) k_f32_to_bf16(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+  pdl_trigger(); pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
 }
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(256) k_embed_lnpre(const float* __restrict__ t
                                                      const float* __restrict__ beta, float* __restrict__ e_out,
                                                      float* __restrict__ x0, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      int S, int T, int D) {
+  pdl_trigger(); pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= S * T) return;
   const int s = row / T, t = row - s * T;
@@ -109,6 +112,7 @@ template <int NCH>
 __global__ void __launch_bounds__(256) k_ln_fwd(const float* __restrict__ x, size_t in_stride, const float* __restrict__ gamma,
                                                 const float* __restrict__ beta, bf16* __restrict__ y, float* __restrict__ mean_out,
                                                 float* __restrict__ rstd_out, int rows, int D) {
+  pdl_trigger(); pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= rows) return;
   constexpr int N = 4 * NCH;
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ dy, co
                                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                 float* __restrict__ dx, bf16* __restrict__ dx_bf16, int rows, int T, int D,
                                                 int mode, int accumulate) {
+  pdl_trigger(); pdl_wait();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   constexpr int N = 4 * NCH;
