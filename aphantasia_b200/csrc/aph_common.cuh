@@ -49,7 +49,7 @@ constexpr int kNumSMs = 148;   // B200
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-bool pdl_enabled();            // api.cu: APH_PDL=0 disables
+bool pdl_enabled();            // api.cu: APH_PDL=1 enables (off by default: no measured gain on top of the graph cache)
 
 // cudaLaunchKernelEx wrapper: optional cluster width and the programmatic-serialization attribute
 template <typename... KArgs, typename... Args>

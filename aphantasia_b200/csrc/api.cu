@@ -15,7 +15,8 @@ void set_error(const char* fmt, ...) {
 }
 bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("APH_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  // opt-in (APH_PDL=1): with the CUDA-graph cache already removing launch gaps it measured 151.2 vs 152.7 steps/s at C2
+  if (v < 0) { const char* e = getenv("APH_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
 }  // namespace aph
