@@ -40,6 +40,7 @@ __device__ __forceinline__ CropParams load_params(const float* __restrict__ row)
   for (int i = 0; i < 8; ++i) p.pc[i] = row[APH_F_PERSP + i];
   p.ei = (int)row[APH_F_ER_I]; p.ej = (int)row[APH_F_ER_J]; p.eh = (int)row[APH_F_ER_H]; p.ew = (int)row[APH_F_ER_W];
   p.r00 = row[APH_F_ROT]; p.r01 = row[APH_F_ROT + 1]; p.r10 = row[APH_F_ROT + 2]; p.r11 = row[APH_F_ROT + 3];
+  if (!(p.flags & APH_FLAG_ERASE)) { p.eh = 0; p.ew = 0; }
   return p;
 }
 
@@ -88,7 +89,13 @@ __device__ __forceinline__ Bilin persp_taps(const CropParams& p, int y, int x, i
   const float n1x = bx * (p.pc[0] / half) + by * (p.pc[1] / half) + (p.pc[2] / half);
   const float n1y = bx * (p.pc[3] / half) + by * (p.pc[4] / half) + (p.pc[5] / half);
   const float den = bx * p.pc[6] + by * p.pc[7] + 1.f;
-  return bilin_taps(n1x / den - 1.f, n1y / den - 1.f, size);
+  const float inv = __fdividef(1.f, den);          // MUFU.RCP (<= 2 ulp); forward and backward share these taps
+  return bilin_taps(n1x * inv - 1.f, n1y * inv - 1.f, size);
+}
+
+// erase rectangle test; an unset flag is folded into an empty rectangle by load_params (eh = ew = 0)
+__device__ __forceinline__ bool erased(const CropParams& p, int y, int x) {
+  return (unsigned)(y - p.ei) < (unsigned)p.eh && (unsigned)(x - p.ej) < (unsigned)p.ew;
 }
 
 __device__ __forceinline__ float tap_dot(const float* __restrict__ A, const Bilin& b, int size) {
@@ -101,9 +108,10 @@ __device__ __forceinline__ float tap_dot(const float* __restrict__ A, const Bili
 }
 
 // value of the post-perspective, post-erase image B at integer pixel (y, x)
+template <bool PERSP>
 __device__ __forceinline__ float stageB(const float* __restrict__ A, const CropParams& p, int y, int x, int size) {
-  if ((p.flags & APH_FLAG_ERASE) && y >= p.ei && y < p.ei + p.eh && x >= p.ej && x < p.ej + p.ew) return 0.f;
-  if (p.flags & APH_FLAG_PERSP) {
+  if (erased(p, y, x)) return 0.f;
+  if (PERSP) {
     const Bilin b = persp_taps(p, y, x, size);
     const float mask = b.w00 + b.w01 + b.w10 + b.w11;
     return tap_dot(A, b, size) * mask;
@@ -135,6 +143,24 @@ __device__ __forceinline__ TapTables build_taps(float* base, const CropParams& p
   return t;
 }
 
+// rotate tap -> erase test -> perspective taps on top of the resized image A, then the CLIP normalisation as one FMA
+template <bool PERSP>
+__device__ __forceinline__ void fwd_compose(const float* __restrict__ A, const CropParams& p, int size, int warp, int lane, int nwarps,
+                                            float inv_sd, float shift, float* __restrict__ o) {
+  for (int i = warp; i < size; i += nwarps) {
+    for (int j = lane; j < size; j += 32) {
+      const Bilin b = rot_taps(p, i, j, size);
+      const float mask = b.w00 + b.w01 + b.w10 + b.w11;
+      float s = 0.f;
+      if (b.w00 != 0.f) s += b.w00 * stageB<PERSP>(A, p, b.y0, b.x0, size);
+      if (b.w01 != 0.f) s += b.w01 * stageB<PERSP>(A, p, b.y0, b.x0 + 1, size);
+      if (b.w10 != 0.f) s += b.w10 * stageB<PERSP>(A, p, b.y0 + 1, b.x0, size);
+      if (b.w11 != 0.f) s += b.w11 * stageB<PERSP>(A, p, b.y0 + 1, b.x0 + 1, size);
+      o[i * size + j] = fmaf(s * mask, inv_sd, shift);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024, 1)
 k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pad_left, const float* __restrict__ table,
              int size, int kind, float* __restrict__ out) {
@@ -147,15 +173,9 @@ k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const TapTables tt = build_taps(A + ((n + 3) & ~3), p, size, H, W, pad_top, pad_left, scale);
   __syncthreads();
-  // ---- stage 1: bicubic resize into shared memory (warp = output row). For each 32-pixel chunk the warp first forms the
-  // VERTICAL 4-tap combination of the contiguous canvas span the chunk touches (coalesced row reads, one wavefront per
-  // load) in a per-warp strip, then every lane takes its 4 horizontal taps from the strip: ~3x fewer L1 wavefronts than 16
-  // gathered loads per pixel. Wrapped frames and very wide spans (scale > ~3.8) use the direct 16-tap form.
-  float* strip = A + ((n + 3) & ~3) + 16 * size + warp * STRIP;
-  // measured on B200 (profiles/r1g): the strip form is SLOWER for the forward (0.68 vs 0.51 ms: two extra warp barriers and
-  // a dependent shared-memory round trip per chunk outweigh the saved L1 wavefronts) -> forward keeps the direct 16-tap form;
-  // the backward (where it removes 45 % of the global atomics) keeps the strip.
-  const bool can_strip = false && (pad_top == 0 && pad_left == 0);
+  // ---- stage 1: bicubic resize into shared memory (warp = output row), direct 16-tap form through the per-CTA tap tables.
+  // (A vertical-first per-warp strip variant was measured SLOWER here, 0.68 vs 0.51 ms, profiles/r1g: two extra warp barriers
+  // and a dependent shared-memory round trip per chunk outweigh the saved L1 wavefronts; the backward keeps its strip.)
   for (int i = warp; i < size; i += nwarps) {
     const int4 yo = *reinterpret_cast<const int4*>(tt.yo + 4 * i);
     const float4 wy = *reinterpret_cast<const float4*>(tt.yw + 4 * i);
@@ -165,59 +185,32 @@ k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pa
       const int jc = min(j, size - 1);
       const int4 xo = *reinterpret_cast<const int4*>(tt.xo + 4 * jc);
       const float4 wx = *reinterpret_cast<const float4*>(tt.xw + 4 * jc);
-      const int xfirst = tt.xo[4 * j0], xlast = tt.xo[4 * min(j0 + 31, size - 1) + 3];
-      const int span = xlast - xfirst + 1;
-      float acc;
-      if (can_strip && span <= STRIP) {
-        for (int x = lane; x < span; x += 32) {
-          float v = wy.x * __ldg(r0 + xfirst + x);
-          v += wy.y * __ldg(r1 + xfirst + x); v += wy.z * __ldg(r2 + xfirst + x); v += wy.w * __ldg(r3 + xfirst + x);
-          strip[x] = v;
-        }
-        __syncwarp();
-        acc = wx.x * strip[xo.x - xfirst];
-        acc += wx.y * strip[xo.y - xfirst]; acc += wx.z * strip[xo.z - xfirst]; acc += wx.w * strip[xo.w - xfirst];
-        __syncwarp();
-      } else {
-        const float v0 = wx.x * __ldg(r0 + xo.x) + wx.y * __ldg(r0 + xo.y) + wx.z * __ldg(r0 + xo.z) + wx.w * __ldg(r0 + xo.w);
-        const float v1 = wx.x * __ldg(r1 + xo.x) + wx.y * __ldg(r1 + xo.y) + wx.z * __ldg(r1 + xo.z) + wx.w * __ldg(r1 + xo.w);
-        const float v2 = wx.x * __ldg(r2 + xo.x) + wx.y * __ldg(r2 + xo.y) + wx.z * __ldg(r2 + xo.z) + wx.w * __ldg(r2 + xo.w);
-        const float v3 = wx.x * __ldg(r3 + xo.x) + wx.y * __ldg(r3 + xo.y) + wx.z * __ldg(r3 + xo.z) + wx.w * __ldg(r3 + xo.w);
-        acc = wy.x * v0;
-        acc += wy.y * v1; acc += wy.z * v2; acc += wy.w * v3;
-      }
+      const float v0 = wx.x * __ldg(r0 + xo.x) + wx.y * __ldg(r0 + xo.y) + wx.z * __ldg(r0 + xo.z) + wx.w * __ldg(r0 + xo.w);
+      const float v1 = wx.x * __ldg(r1 + xo.x) + wx.y * __ldg(r1 + xo.y) + wx.z * __ldg(r1 + xo.z) + wx.w * __ldg(r1 + xo.w);
+      const float v2 = wx.x * __ldg(r2 + xo.x) + wx.y * __ldg(r2 + xo.y) + wx.z * __ldg(r2 + xo.z) + wx.w * __ldg(r2 + xo.w);
+      const float v3 = wx.x * __ldg(r3 + xo.x) + wx.y * __ldg(r3 + xo.y) + wx.z * __ldg(r3 + xo.z) + wx.w * __ldg(r3 + xo.w);
+      float acc = wy.x * v0;
+      acc += wy.y * v1; acc += wy.z * v2; acc += wy.w * v3;
       if (j < size) A[i * size + j] = acc;
     }
   }
   __syncthreads();
-  // ---- stages 2-5 by tap composition
+  // ---- stages 2-5 by tap composition (the perspective branch is CTA-uniform: specialised loops)
   float* o = out + ((size_t)crop * 3 + ch) * n;
-  const float mean = c_mean[ch], sd = c_std[ch];
-  for (int i = warp; i < size; i += nwarps) {
-    for (int j = lane; j < size; j += 32) {
-      const int idx = i * size + j;
-      float v;
-      if (kind == APH_TF_FAST) {
-        const Bilin b = rot_taps(p, i, j, size);
-        const float mask = b.w00 + b.w01 + b.w10 + b.w11;
-        float s = 0.f;
-        if (b.w00 != 0.f) s += b.w00 * stageB(A, p, b.y0, b.x0, size);
-        if (b.w01 != 0.f) s += b.w01 * stageB(A, p, b.y0, b.x0 + 1, size);
-        if (b.w10 != 0.f) s += b.w10 * stageB(A, p, b.y0 + 1, b.x0, size);
-        if (b.w11 != 0.f) s += b.w11 * stageB(A, p, b.y0 + 1, b.x0 + 1, size);
-        v = s * mask;
-      } else {
-        v = A[idx];
-      }
-      if (kind != APH_TF_NONE) v = (v - mean) / sd;
-      o[idx] = v;
-    }
+  const float inv_sd = 1.f / c_std[ch], shift = -c_mean[ch] * inv_sd;
+  if (kind == APH_TF_FAST) {
+    if (p.flags & APH_FLAG_PERSP) fwd_compose<true>(A, p, size, warp, lane, nwarps, inv_sd, shift, o);
+    else fwd_compose<false>(A, p, size, warp, lane, nwarps, inv_sd, shift, o);
+  } else {
+    const float a = (kind != APH_TF_NONE) ? inv_sd : 1.f, b = (kind != APH_TF_NONE) ? shift : 0.f;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) o[idx] = fmaf(A[idx], a, b);
   }
 }
 
+template <bool PERSP>
 __device__ __forceinline__ void scatterB(float* __restrict__ gA, const CropParams& p, int y, int x, int size, float g) {
-  if ((p.flags & APH_FLAG_ERASE) && y >= p.ei && y < p.ei + p.eh && x >= p.ej && x < p.ej + p.ew) return;
-  if (p.flags & APH_FLAG_PERSP) {
+  if (erased(p, y, x)) return;
+  if (PERSP) {
     const Bilin b = persp_taps(p, y, x, size);
     const float gm = g * (b.w00 + b.w01 + b.w10 + b.w11);
     if (b.w00 != 0.f) atomicAdd(&gA[b.y0 * size + b.x0], gm * b.w00);
@@ -226,6 +219,26 @@ __device__ __forceinline__ void scatterB(float* __restrict__ gA, const CropParam
     if (b.w11 != 0.f) atomicAdd(&gA[(b.y0 + 1) * size + b.x0 + 1], gm * b.w11);
   } else {
     atomicAdd(&gA[y * size + x], g);
+  }
+}
+
+// adjoint of normalise -> rotate -> erase -> perspective: scatters grad_out of one (crop, channel) into the shared gradient image
+template <bool PERSP>
+__device__ __forceinline__ void bwd_compose(float* __restrict__ gA, const float* __restrict__ go, const CropParams& p, int size,
+                                            int warp, int lane, int nwarps, float inv_sd) {
+  for (int i = warp; i < size; i += nwarps) {
+    float gnext = (lane < size) ? go[i * size + lane] : 0.f;
+    for (int j = lane; j < size; j += 32) {
+      const float graw = gnext;
+      if (j + 32 < size) gnext = go[i * size + j + 32];            // next chunk's load overlaps this chunk's scatter
+      const Bilin b = rot_taps(p, i, j, size);
+      const float g = graw * inv_sd * (b.w00 + b.w01 + b.w10 + b.w11);
+      if (g == 0.f) continue;
+      if (b.w00 != 0.f) scatterB<PERSP>(gA, p, b.y0, b.x0, size, g * b.w00);
+      if (b.w01 != 0.f) scatterB<PERSP>(gA, p, b.y0, b.x0 + 1, size, g * b.w01);
+      if (b.w10 != 0.f) scatterB<PERSP>(gA, p, b.y0 + 1, b.x0, size, g * b.w10);
+      if (b.w11 != 0.f) scatterB<PERSP>(gA, p, b.y0 + 1, b.x0 + 1, size, g * b.w11);
+    }
   }
 }
 
@@ -241,20 +254,13 @@ k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int 
   const float inv_sd = (kind != APH_TF_NONE) ? 1.f / c_std[ch] : 1.f;
   const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
   const TapTables tt = build_taps(gA + ((n + 3) & ~3), p, size, H, W, pad_top, pad_left, scale);
+  float* strip = gA + ((n + 3) & ~3) + 16 * size + warp * STRIP;
+  for (int x = lane; x < STRIP; x += 32) strip[x] = 0.f;           // the strip is re-zeroed as it is drained below
   if (kind == APH_TF_FAST) {
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = 0.f;
     __syncthreads();
-    for (int i = warp; i < size; i += nwarps) {
-      for (int j = lane; j < size; j += 32) {
-        const Bilin b = rot_taps(p, i, j, size);
-        const float g = go[i * size + j] / c_std[ch] * (b.w00 + b.w01 + b.w10 + b.w11);
-        if (g == 0.f) continue;
-        if (b.w00 != 0.f) scatterB(gA, p, b.y0, b.x0, size, g * b.w00);
-        if (b.w01 != 0.f) scatterB(gA, p, b.y0, b.x0 + 1, size, g * b.w01);
-        if (b.w10 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0, size, g * b.w10);
-        if (b.w11 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0 + 1, size, g * b.w11);
-      }
-    }
+    if (p.flags & APH_FLAG_PERSP) bwd_compose<true>(gA, go, p, size, warp, lane, nwarps, inv_sd);
+    else bwd_compose<false>(gA, go, p, size, warp, lane, nwarps, inv_sd);
   } else {
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = go[idx] * inv_sd;
   }
@@ -263,7 +269,6 @@ k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int 
   // strip (shared atomics, the lanes' 4-tap windows overlap), then the strip is scattered to the 4 source rows with
   // COALESCED global red.add (4 x span instead of 16 x 32 scattered atomics per chunk).
   float* gc = grad_canvas + (size_t)ch * H * W;
-  float* strip = gA + ((n + 3) & ~3) + 16 * size + warp * STRIP;
   const bool can_strip = (pad_top == 0 && pad_left == 0);
   for (int i = warp; i < size; i += nwarps) {
     const int4 yo = *reinterpret_cast<const int4*>(tt.yo + 4 * i);
@@ -279,8 +284,6 @@ k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int 
       const int xfirst = tt.xo[4 * j0], xlast = tt.xo[4 * min(j0 + 31, size - 1) + 3];
       const int span = xlast - xfirst + 1;
       if (can_strip && span <= STRIP) {
-        for (int x = lane; x < span; x += 32) strip[x] = 0.f;
-        __syncwarp();
         if (g != 0.f) {
           atomicAdd(&strip[xo.x - xfirst], g * wx.x); atomicAdd(&strip[xo.y - xfirst], g * wx.y);
           atomicAdd(&strip[xo.z - xfirst], g * wx.z); atomicAdd(&strip[xo.w - xfirst], g * wx.w);
@@ -289,6 +292,7 @@ k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int 
         for (int x = lane; x < span; x += 32) {
           const float h = strip[x];
           if (h != 0.f) {
+            strip[x] = 0.f;
 #pragma unroll
             for (int a = 0; a < 4; ++a) atomicAdd(gc + yoff[a] + xfirst + x, wya[a] * h);
           }
@@ -325,17 +329,9 @@ k_sample_bwd_stage1(const float* __restrict__ grad_out, const float* __restrict_
   const float* go = grad_out + ((size_t)crop * 3 + ch) * n;
   for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = 0.f;
   __syncthreads();
-  for (int i = warp; i < size; i += nwarps) {
-    for (int j = lane; j < size; j += 32) {
-      const Bilin b = rot_taps(p, i, j, size);
-      const float g = go[i * size + j] / c_std[ch] * (b.w00 + b.w01 + b.w10 + b.w11);
-      if (g == 0.f) continue;
-      if (b.w00 != 0.f) scatterB(gA, p, b.y0, b.x0, size, g * b.w00);
-      if (b.w01 != 0.f) scatterB(gA, p, b.y0, b.x0 + 1, size, g * b.w01);
-      if (b.w10 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0, size, g * b.w10);
-      if (b.w11 != 0.f) scatterB(gA, p, b.y0 + 1, b.x0 + 1, size, g * b.w11);
-    }
-  }
+  const float inv_sd = 1.f / c_std[ch];
+  if (p.flags & APH_FLAG_PERSP) bwd_compose<true>(gA, go, p, size, warp, lane, nwarps, inv_sd);
+  else bwd_compose<false>(gA, go, p, size, warp, lane, nwarps, inv_sd);
   __syncthreads();
   float* o = gA_out + ((size_t)crop * 3 + ch) * n;
   for (int idx = threadIdx.x; idx < n; idx += blockDim.x) o[idx] = gA[idx];
