@@ -354,46 +354,39 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 1) k_attn_bwd_tc(const 
 // ---------------------------------------------------------------------------------------------
 // Pipelined variants for T <= 64 (ViT-B/32: T = 50): the per-(sample, head) problem is so small that a CTA is dominated by
 // the global-load latency of its 24-32 KB of operands (ncu: long-scoreboard stalls, 17 % warps active). Here a CTA walks a
-// strided list of (sample, head) items and prefetches the NEXT item's tiles with cp.async (zero-filled tail rows) into the
-// other half of a double buffer while it computes the current one.
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gptr), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void load_tile64_async(uint32_t tile, const bf16* __restrict__ src, size_t ld, int rows, int valid, int nthreads) {
-  for (int idx = threadIdx.x; idx < rows * 8; idx += nthreads) {
-    const int r = idx >> 3, c = idx & 7;
-    const bool ok = r < valid;
-    cp_async16(tile + swz(r, c, 128), reinterpret_cast<const uint4*>(src + (size_t)(ok ? r : 0) * ld) + c, ok ? 16 : 0);
-  }
-}
-
+// strided list of (sample, head) items and prefetches the NEXT item's tiles into the other half of a double buffer while it
+// computes the current one. The tiles are fetched by TMA (one thread, 3-4 cp.async.bulk.tensor.3d per item, completion on an
+// mbarrier) from a [S][T][cols] view of the token matrix whose out-of-range token rows arrive zero-filled; the per-thread
+// cp.async loop this replaced was 20 % of the backward kernel's instructions (profiles/r1l_ncu_full_summary.md).
 template <int NT2>
-__global__ void __launch_bounds__(128) k_attn_fwd_tc1(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int D, int heads, int items) {
+__global__ void __launch_bounds__(128) k_attn_fwd_tc1(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
+                                                      bf16* __restrict__ out, int T, int D, int heads, int items) {
   pdl_trigger(); pdl_wait();
-  extern __shared__ __align__(128) uint8_t sm[];
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  __shared__ __align__(8) uint64_t full[2];
   constexpr int TK = NT2 * 16, QB = 64, BUF = (2 * TK + QB) * 128;
+  const uint32_t sm_a = (smem_u32(sm_raw) + 1023u) & ~1023u;     // 128B-swizzled TMA tiles want 1024-byte aligned bases
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const size_t ld = (size_t)3 * D;
+  if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); fence_barrier_init(); tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_q); }
+  __syncthreads();
+  // one thread asks TMA for the K, V, Q tiles of an item: rows >= T of the 3-D view come back as zeros
   auto issue = [&](int item, int b) {
     const int s = item / heads, h = item - s * heads;
-    const bf16* base = qkv + (size_t)s * T * ld + h * 64;
-    const uint32_t a = smem_u32(sm + b * BUF);
-    load_tile64_async(a, base + D, ld, TK, T, 128);
-    load_tile64_async(a + TK * 128, base + 2 * D, ld, TK, T, 128);
-    load_tile64_async(a + 2 * TK * 128, base, ld, QB, T, 128);
-    cp_async_commit();
+    const uint32_t a = sm_a + b * BUF;
+    mbar_expect_tx(&full[b], BUF);
+    tma_load_3d(a, &tm_kv, &full[b], D + h * 64, 0, s);
+    tma_load_3d(a + TK * 128, &tm_kv, &full[b], 2 * D + h * 64, 0, s);
+    tma_load_3d(a + 2 * TK * 128, &tm_q, &full[b], h * 64, 0, s);
   };
   int item = blockIdx.x, b = 0;
-  if (item < items) issue(item, 0);
+  uint32_t phases = 0u;                                          // bit b = parity of the next fill of buffer b
+  if (item < items && threadIdx.x == 0) issue(item, 0);
   for (; item < items; item += gridDim.x, b ^= 1) {
     const int nxt = item + gridDim.x;
-    if (nxt < items) { issue(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
+    if (nxt < items && threadIdx.x == 0) issue(nxt, b ^ 1);      // buffer b^1 was released by the barrier that ended the previous item
+    mbar_wait(&full[b], (phases >> b) & 1u); phases ^= 1u << b;
     const int s = item / heads, h = item - s * heads;
-    const uint32_t ks_a = smem_u32(sm + b * BUF), vs_a = ks_a + TK * 128, qs_a = vs_a + TK * 128;
+    const uint32_t ks_a = sm_a + b * BUF, vs_a = ks_a + TK * 128, qs_a = vs_a + TK * 128;
     const int r0 = warp * 16;
     if (r0 < T) {
       uint32_t qa[4][4];
@@ -443,34 +436,43 @@ __global__ void __launch_bounds__(128) k_attn_fwd_tc1(const bf16* __restrict__ q
 }
 
 template <int NT2>
-__global__ void __launch_bounds__(128, 2) k_attn_bwd_tc1(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, bf16* __restrict__ dqkv,
+__global__ void __launch_bounds__(128, 2) k_attn_bwd_tc1(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
+                                                         const __grid_constant__ CUtensorMap tm_do, bf16* __restrict__ dqkv,
                                                          int T, int D, int heads, int items) {
   pdl_trigger(); pdl_wait();
-  extern __shared__ __align__(128) uint8_t sm[];
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  __shared__ __align__(8) uint64_t full[2];
   constexpr int TK = NT2 * 16, QB = 64, PB = 128, BUF = (2 * TK + 2 * QB) * 128;
+  uint8_t* sm = sm_raw + (((smem_u32(sm_raw) + 1023u) & ~1023u) - smem_u32(sm_raw));
+  const uint32_t sm_a = smem_u32(sm);
   uint8_t* Ps = sm + 2 * BUF; uint8_t* Ds = Ps + QB * PB;
   const uint32_t ps_a = smem_u32(Ps), ds_a = smem_u32(Ds);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const size_t ld = (size_t)3 * D;
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1); fence_barrier_init();
+    tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do);
+  }
+  __syncthreads();
   auto issue = [&](int item, int b) {
     const int s = item / heads, h = item - s * heads;
-    const bf16* base = qkv + (size_t)s * T * ld + h * 64;
-    const uint32_t a = smem_u32(sm + b * BUF);
-    load_tile64_async(a, base + D, ld, TK, T, 128);
-    load_tile64_async(a + TK * 128, base + 2 * D, ld, TK, T, 128);
-    load_tile64_async(a + 2 * TK * 128, base, ld, QB, T, 128);
-    load_tile64_async(a + (2 * TK + QB) * 128, dout + (size_t)s * T * D + h * 64, (size_t)D, QB, T, 128);
-    cp_async_commit();
+    const uint32_t a = sm_a + b * BUF;
+    mbar_expect_tx(&full[b], BUF);
+    tma_load_3d(a, &tm_kv, &full[b], D + h * 64, 0, s);
+    tma_load_3d(a + TK * 128, &tm_kv, &full[b], 2 * D + h * 64, 0, s);
+    tma_load_3d(a + 2 * TK * 128, &tm_q, &full[b], h * 64, 0, s);
+    tma_load_3d(a + (2 * TK + QB) * 128, &tm_do, &full[b], h * 64, 0, s);
   };
   int item = blockIdx.x, b = 0;
-  if (item < items) issue(item, 0);
+  uint32_t phases = 0u;                                          // bit b = parity of the next fill of buffer b
+  if (item < items && threadIdx.x == 0) issue(item, 0);
   for (; item < items; item += gridDim.x, b ^= 1) {
     const int nxt = item + gridDim.x;
-    if (nxt < items) { issue(nxt, b ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
+    if (nxt < items && threadIdx.x == 0) issue(nxt, b ^ 1);
+    mbar_wait(&full[b], (phases >> b) & 1u); phases ^= 1u << b;
     const int s = item / heads, h = item - s * heads;
     bf16* obase = dqkv + (size_t)s * T * ld + h * 64;
-    const uint32_t ks_a = smem_u32(sm + b * BUF), vs_a = ks_a + TK * 128, qs_a = vs_a + TK * 128, gs_a = qs_a + QB * 128;
+    const uint32_t ks_a = sm_a + b * BUF, vs_a = ks_a + TK * 128, qs_a = vs_a + TK * 128, gs_a = qs_a + QB * 128;
     const int r0 = warp * 16;
     {
       uint32_t qa[4][4], ga[4][4];
@@ -565,8 +567,8 @@ __global__ void __launch_bounds__(128, 2) k_attn_bwd_tc1(const bf16* __restrict_
 
 template <int NT2>
 static int attn_launch1(bool fwd, const bf16* qkv, const bf16* dout, bf16* out_or_dqkv, int S, int T, int D, int heads, cudaStream_t st) {
-  constexpr size_t smem_f = (size_t)2 * (2 * NT2 * 16 + 64) * 128;
-  constexpr size_t smem_b = (size_t)2 * (2 * NT2 * 16 + 128) * 128 + (size_t)2 * 64 * 128;
+  constexpr size_t smem_f = (size_t)2 * (2 * NT2 * 16 + 64) * 128 + 1024;                                // + alignment slack
+  constexpr size_t smem_b = (size_t)2 * (2 * NT2 * 16 + 128) * 128 + (size_t)2 * 64 * 128 + 1024;
   static bool cfg = false;
   if (!cfg) {
     APH_CUDA_OK(cudaFuncSetAttribute(k_attn_fwd_tc1<NT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
@@ -576,14 +578,18 @@ static int attn_launch1(bool fwd, const bf16* qkv, const bf16* dout, bf16* out_o
     cfg = true;
   }
   const int items = S * heads;
+  CUtensorMap tm_kv, tm_q, tm_do;
+  if (int e = make_tmap_bf16_tokens(&tm_kv, qkv, 3 * D, T, S, NT2 * 16)) return e;
+  if (int e = make_tmap_bf16_tokens(&tm_q, qkv, 3 * D, T, S, 64)) return e;
   if (fwd) {
     const int per_sm = (int)(220 * 1024 / smem_f) < 6 ? (int)(220 * 1024 / smem_f) : 6;
     const int grid = items < kNumSMs * per_sm ? items : kNumSMs * per_sm;
-    APH_CUDA_OK(launch_k(k_attn_fwd_tc1<NT2>, dim3(grid), dim3(128), smem_f, st, 1, qkv, out_or_dqkv, T, D, heads, items));
+    APH_CUDA_OK(launch_k(k_attn_fwd_tc1<NT2>, dim3(grid), dim3(128), smem_f, st, 1, tm_kv, tm_q, out_or_dqkv, T, D, heads, items));
   } else {
+    if (int e = make_tmap_bf16_tokens(&tm_do, dout, D, T, S, 64)) return e;
     const int per_sm = (int)(220 * 1024 / smem_b) < 3 ? (int)(220 * 1024 / smem_b) : 3;
     const int grid = items < kNumSMs * per_sm ? items : kNumSMs * per_sm;
-    APH_CUDA_OK(launch_k(k_attn_bwd_tc1<NT2>, dim3(grid), dim3(128), smem_b, st, 1, qkv, dout, out_or_dqkv, T, D, heads, items));
+    APH_CUDA_OK(launch_k(k_attn_bwd_tc1<NT2>, dim3(grid), dim3(128), smem_b, st, 1, tm_kv, tm_q, tm_do, out_or_dqkv, T, D, heads, items));
   }
   APH_LAUNCH_OK();
   return 0;

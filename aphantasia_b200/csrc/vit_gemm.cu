@@ -38,6 +38,23 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int K, int box_
   return 0;
 }
 
+// 3-D view [S][T][cols] of a token-major bf16 matrix [S*T, cols]: a box of `box_rows` tokens x 64 columns of ONE sample; rows past T
+// are out of bounds in the T dimension and arrive zero-filled (the attention kernels rely on that for their padded tiles).
+int make_tmap_bf16_tokens(CUtensorMap* out, const void* base, int cols, int T, int S, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  APH_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  APH_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && cols % 8 == 0, "tensor map: base/stride not 16-byte aligned");
+  const cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)S};
+  const cuuint64_t gstride[2] = {(cuuint64_t)cols * 2, (cuuint64_t)T * cols * 2};
+  const cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  APH_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (tokens) failed: CUresult %d (cols=%d T=%d S=%d box_rows=%d)", (int)r, cols, T, S, box_rows);
+  return 0;
+}
+
 // ---- optional per-launch event timing (bench.py's roofline: the GEMM kernel's real time inside a step)
 static bool g_prof = false;
 bool gemm_profiling_on() { return g_prof; }
