@@ -207,43 +207,170 @@ k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pa
   }
 }
 
-template <bool PERSP>
+// Shared-memory accumulation cell. fp32 atomicAdd on shared memory is a compare-and-swap loop on this architecture
+// (SASS: ATOMS.CAST.SPIN, ~6 instructions and two dependent shared round trips per add; ncu: 31 % of the backward kernel's
+// instructions, 44 % of its stall samples). The opt-in FIXED form (k_sample_bwd, APH_SAMPLE_BWD_FIXED=1) accumulates round(v * scale) with the native integer ATOMS.ADD instead; the
+// scale is chosen per (crop, channel) from the block maximum so the sum cannot overflow, and the result is order-independent.
+template <bool FIXED>
+__device__ __forceinline__ void acc_add(float* __restrict__ cell, float v) {
+  if (FIXED) atomicAdd(reinterpret_cast<int*>(cell), __float2int_rn(v));
+  else atomicAdd(cell, v);
+}
+
+template <bool PERSP, bool FIXED>
 __device__ __forceinline__ void scatterB(float* __restrict__ gA, const CropParams& p, int y, int x, int size, float g) {
   if (erased(p, y, x)) return;
   if (PERSP) {
     const Bilin b = persp_taps(p, y, x, size);
     const float gm = g * (b.w00 + b.w01 + b.w10 + b.w11);
-    if (b.w00 != 0.f) atomicAdd(&gA[b.y0 * size + b.x0], gm * b.w00);
-    if (b.w01 != 0.f) atomicAdd(&gA[b.y0 * size + b.x0 + 1], gm * b.w01);
-    if (b.w10 != 0.f) atomicAdd(&gA[(b.y0 + 1) * size + b.x0], gm * b.w10);
-    if (b.w11 != 0.f) atomicAdd(&gA[(b.y0 + 1) * size + b.x0 + 1], gm * b.w11);
+    if (b.w00 != 0.f) acc_add<FIXED>(&gA[b.y0 * size + b.x0], gm * b.w00);
+    if (b.w01 != 0.f) acc_add<FIXED>(&gA[b.y0 * size + b.x0 + 1], gm * b.w01);
+    if (b.w10 != 0.f) acc_add<FIXED>(&gA[(b.y0 + 1) * size + b.x0], gm * b.w10);
+    if (b.w11 != 0.f) acc_add<FIXED>(&gA[(b.y0 + 1) * size + b.x0 + 1], gm * b.w11);
   } else {
-    atomicAdd(&gA[y * size + x], g);
+    acc_add<FIXED>(&gA[y * size + x], g);
   }
 }
 
-// adjoint of normalise -> rotate -> erase -> perspective: scatters grad_out of one (crop, channel) into the shared gradient image
-template <bool PERSP>
+// adjoint of normalise -> rotate -> erase -> perspective: scatters grad_out of one (crop, channel) into the shared gradient
+// image. `gscale` = 1/std (fp32 cells) or fixed_scale/std (integer cells).
+template <bool PERSP, bool FIXED>
 __device__ __forceinline__ void bwd_compose(float* __restrict__ gA, const float* __restrict__ go, const CropParams& p, int size,
-                                            int warp, int lane, int nwarps, float inv_sd) {
+                                            int warp, int lane, int nwarps, float gscale) {
   for (int i = warp; i < size; i += nwarps) {
     float gnext = (lane < size) ? go[i * size + lane] : 0.f;
     for (int j = lane; j < size; j += 32) {
       const float graw = gnext;
       if (j + 32 < size) gnext = go[i * size + j + 32];            // next chunk's load overlaps this chunk's scatter
       const Bilin b = rot_taps(p, i, j, size);
-      const float g = graw * inv_sd * (b.w00 + b.w01 + b.w10 + b.w11);
+      const float g = graw * gscale * (b.w00 + b.w01 + b.w10 + b.w11);
       if (g == 0.f) continue;
-      if (b.w00 != 0.f) scatterB<PERSP>(gA, p, b.y0, b.x0, size, g * b.w00);
-      if (b.w01 != 0.f) scatterB<PERSP>(gA, p, b.y0, b.x0 + 1, size, g * b.w01);
-      if (b.w10 != 0.f) scatterB<PERSP>(gA, p, b.y0 + 1, b.x0, size, g * b.w10);
-      if (b.w11 != 0.f) scatterB<PERSP>(gA, p, b.y0 + 1, b.x0 + 1, size, g * b.w11);
+      if (b.w00 != 0.f) scatterB<PERSP, FIXED>(gA, p, b.y0, b.x0, size, g * b.w00);
+      if (b.w01 != 0.f) scatterB<PERSP, FIXED>(gA, p, b.y0, b.x0 + 1, size, g * b.w01);
+      if (b.w10 != 0.f) scatterB<PERSP, FIXED>(gA, p, b.y0 + 1, b.x0, size, g * b.w10);
+      if (b.w11 != 0.f) scatterB<PERSP, FIXED>(gA, p, b.y0 + 1, b.x0 + 1, size, g * b.w11);
+    }
+  }
+}
+
+// block-wide maximum (all threads get it); `red` = 32 floats of shared scratch
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float m = (threadIdx.x & 31) < (blockDim.x >> 5) ? red[threadIdx.x & 31] : 0.f;
+  return warp_max(m);
+}
+
+// bicubic adjoint of the shared gradient image gA into the canvas gradient. Per 32-pixel chunk of a gradient row the horizontal
+// taps are first accumulated into a per-warp strip (the lanes' 4-tap windows overlap), then the strip is scattered to the 4
+// source rows with COALESCED global red.add (4 x span instead of 16 x 32 scattered atomics per chunk).
+template <bool FIXED>
+__device__ __forceinline__ void bwd_bicubic(const float* __restrict__ gA, float* __restrict__ strip, const TapTables& tt, float* __restrict__ gc,
+                                            int size, int warp, int lane, int nwarps, bool can_strip, float sscale, float inv_sscale) {
+  for (int i = warp; i < size; i += nwarps) {
+    const int4 yo = *reinterpret_cast<const int4*>(tt.yo + 4 * i);
+    const float4 wy = *reinterpret_cast<const float4*>(tt.yw + 4 * i);
+    const int yoff[4] = {yo.x, yo.y, yo.z, yo.w};
+    const float wya[4] = {wy.x, wy.y, wy.z, wy.w};
+    for (int j0 = 0; j0 < size; j0 += 32) {
+      const int j = j0 + lane;
+      const float g = (j < size) ? gA[i * size + j] : 0.f;
+      const int jc = min(j, size - 1);
+      const int4 xo = *reinterpret_cast<const int4*>(tt.xo + 4 * jc);
+      const float4 wx = *reinterpret_cast<const float4*>(tt.xw + 4 * jc);
+      const int xfirst = tt.xo[4 * j0], xlast = tt.xo[4 * min(j0 + 31, size - 1) + 3];
+      const int span = xlast - xfirst + 1;
+      if (can_strip && span <= STRIP) {
+        if (g != 0.f) {
+          const float gs = FIXED ? g * sscale : g;
+          acc_add<FIXED>(&strip[xo.x - xfirst], gs * wx.x); acc_add<FIXED>(&strip[xo.y - xfirst], gs * wx.y);
+          acc_add<FIXED>(&strip[xo.z - xfirst], gs * wx.z); acc_add<FIXED>(&strip[xo.w - xfirst], gs * wx.w);
+        }
+        __syncwarp();
+        for (int x = lane; x < span; x += 32) {
+          const float raw = strip[x];                                // all-zero bits in either representation = nothing landed here
+          if (__float_as_int(raw) != 0) {
+            strip[x] = 0.f;
+            const float h = FIXED ? (float)__float_as_int(raw) * inv_sscale : raw;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) atomicAdd(gc + yoff[a] + xfirst + x, wya[a] * h);
+          }
+        }
+        __syncwarp();
+      } else if (g != 0.f) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          float* r = gc + yoff[a];
+          const float gy = g * wya[a];
+          atomicAdd(r + xo.x, gy * wx.x); atomicAdd(r + xo.y, gy * wx.y); atomicAdd(r + xo.z, gy * wx.z); atomicAdd(r + xo.w, gy * wx.w);
+        }
+      }
     }
   }
 }
 
 __global__ void __launch_bounds__(1024, 1)
 k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int pad_left, const float* __restrict__ table,
+             int size, int kind, float* __restrict__ grad_canvas) {
+  extern __shared__ float gA[];
+  __shared__ float red[32];
+  const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
+  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  const int n = size * size;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float* go = grad_out + ((size_t)crop * 3 + ch) * n;
+  const float inv_sd = (kind != APH_TF_NONE) ? 1.f / c_std[ch] : 1.f;
+  const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
+  const TapTables tt = build_taps(gA + ((n + 3) & ~3), p, size, H, W, pad_top, pad_left, scale);
+  float* strip = gA + ((n + 3) & ~3) + 16 * size + warp * STRIP;
+  for (int x = lane; x < STRIP; x += 32) strip[x] = 0.f;           // the strip is re-zeroed as it is drained
+  // block maximum of |grad_out| sizes the fixed-point scale (NaN / Inf -> INFINITY: fmaxf alone would drop a NaN); the same pass
+  // clears (or, without transforms, fills) gA
+  float amax = 0.f;
+  if (kind == APH_TF_FAST) {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) { const float a = fabsf(go[idx]); amax = (a <= 3e38f) ? fmaxf(amax, a) : INFINITY; gA[idx] = 0.f; }
+  } else {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) { const float v = go[idx] * inv_sd, a = fabsf(v); amax = (a <= 3e38f) ? fmaxf(amax, a) : INFINITY; gA[idx] = v; }
+  }
+  amax = block_max(amax, red);                                      // (contains the block barriers)
+  if (amax == 0.f) return;                                          // nothing to add (block-uniform)
+  float* gc = grad_canvas + (size_t)ch * H * W;
+  const bool can_strip = (pad_top == 0 && pad_left == 0);
+  if (!(amax < 1e30f)) {                                            // Inf / NaN upstream: poison this crop's footprint, as fp32 would
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = __int_as_float(0x7fc00000);
+    __syncthreads();
+    bwd_bicubic<true>(gA, strip, tt, gc, size, warp, lane, nwarps, false, 1.f, 1.f);
+    return;
+  }
+  float gmax = amax;                                                // bound on |gA| for the strip scale
+  if (kind == APH_TF_FAST) {
+    amax *= inv_sd;
+    const bool persp = (p.flags & APH_FLAG_PERSP) != 0;
+    // fan-in bound of one gradient cell: a rotation (area preserving) lands <= 8 weighted samples on a pixel, a perspective
+    // warp of distortion <= 0.5 compresses area by far less than the extra 32x allowed here
+    const float s1 = 2147483648.f / ((persp ? 512.f : 16.f) * amax);
+    if (persp) bwd_compose<true, true>(gA, go, p, size, warp, lane, nwarps, inv_sd * s1);
+    else bwd_compose<false, true>(gA, go, p, size, warp, lane, nwarps, inv_sd * s1);
+    __syncthreads();
+    const float inv_s1 = 1.f / s1;
+    float m = 0.f;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {       // integer cells -> fp32 in place, and their maximum
+      const float v = (float)__float_as_int(gA[idx]) * inv_s1;
+      gA[idx] = v; m = fmaxf(m, fabsf(v));
+    }
+    gmax = block_max(m, red);
+    if (gmax == 0.f) return;
+  }
+  // a strip cell sums <= 4 / min(scale, 1) horizontal taps of |weight| <= 1.2: 64x headroom covers crops down to size / 12
+  const float s2 = 1073741824.f / (64.f * gmax);
+  bwd_bicubic<true>(gA, strip, tt, gc, size, warp, lane, nwarps, can_strip && scale >= 0.08f, s2, 1.f / s2);
+}
+
+// Default backward: fp32 shared accumulation (compare-and-swap loops in SASS).
+__global__ void __launch_bounds__(1024, 1)
+k_sample_bwd_cas(const float* __restrict__ grad_out, int H, int W, int pad_top, int pad_left, const float* __restrict__ table,
              int size, int kind, float* __restrict__ grad_canvas) {
   extern __shared__ float gA[];
   const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
@@ -259,8 +386,8 @@ k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int 
   if (kind == APH_TF_FAST) {
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = 0.f;
     __syncthreads();
-    if (p.flags & APH_FLAG_PERSP) bwd_compose<true>(gA, go, p, size, warp, lane, nwarps, inv_sd);
-    else bwd_compose<false>(gA, go, p, size, warp, lane, nwarps, inv_sd);
+    if (p.flags & APH_FLAG_PERSP) bwd_compose<true, false>(gA, go, p, size, warp, lane, nwarps, inv_sd);
+    else bwd_compose<false, false>(gA, go, p, size, warp, lane, nwarps, inv_sd);
   } else {
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = go[idx] * inv_sd;
   }
@@ -330,8 +457,8 @@ k_sample_bwd_stage1(const float* __restrict__ grad_out, const float* __restrict_
   for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = 0.f;
   __syncthreads();
   const float inv_sd = 1.f / c_std[ch];
-  if (p.flags & APH_FLAG_PERSP) bwd_compose<true>(gA, go, p, size, warp, lane, nwarps, inv_sd);
-  else bwd_compose<false>(gA, go, p, size, warp, lane, nwarps, inv_sd);
+  if (p.flags & APH_FLAG_PERSP) bwd_compose<true, false>(gA, go, p, size, warp, lane, nwarps, inv_sd);
+  else bwd_compose<false, false>(gA, go, p, size, warp, lane, nwarps, inv_sd);
   __syncthreads();
   float* o = gA_out + ((size_t)crop * 3 + ch) * n;
   for (int idx = threadIdx.x; idx < n; idx += blockDim.x) o[idx] = gA[idx];
@@ -421,7 +548,7 @@ using namespace aph;
 
 static int check_sample_args(const char* who, int H, int W, int S, int size, int kind) {
   APH_REQUIRE(H > 0 && W > 0 && S >= 0 && size > 0, "%s: bad shape H=%d W=%d S=%d size=%d", who, H, W, S, size);
-  APH_REQUIRE(((size_t)size * size + 4 + 16 * (size_t)size + 32 * STRIP) * sizeof(float) <= 227 * 1024, "%s: size=%d does not fit one CTA's shared memory (max 231)", who, size);
+  APH_REQUIRE(((size_t)size * size + 4 + 16 * (size_t)size + 32 * STRIP) * sizeof(float) <= 227 * 1024, "%s: size=%d does not fit one CTA's shared memory (max 224)", who, size);
   APH_REQUIRE(kind >= APH_TF_NONE && kind <= APH_TF_FAST, "%s: unknown transform kind %d", who, kind);
   return 0;
 }
@@ -431,7 +558,7 @@ extern "C" int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, in
   if (int e = check_sample_args("aph_sample_fwd", H, W, S, size, kind)) return e;
   if (S == 0) return 0;
   APH_REQUIRE(canvas && table && out, "aph_sample_fwd: null pointer");
-  const size_t smem = ((size_t)size * size + 4 + 16 * (size_t)size + 32 * STRIP) * sizeof(float);
+  const size_t smem = ((size_t)size * size + 4 + 16 * (size_t)size) * sizeof(float);   // no strips in the forward: the rest stays L1
   static size_t configured = 0;
   if (smem > configured) {
     APH_CUDA_OK(cudaFuncSetAttribute(k_sample_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -494,9 +621,15 @@ extern "C" int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, 
   static size_t configured = 0;
   if (smem > configured) {
     APH_CUDA_OK(cudaFuncSetAttribute(k_sample_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_sample_bwd_cas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  k_sample_bwd<<<S * 3, 1024, smem, (cudaStream_t)stream>>>(grad_out, H, W, pad_top, pad_left, table, size, kind, grad_canvas);
+  // APH_SAMPLE_BWD_FIXED=1: integer fixed-point shared accumulation (order-independent shared stage). Measured equal to the
+  // fp32 compare-and-swap kernel (0.581 vs 0.578 ms at C2, profiles/README.md), so the plain fp32 kernel stays the default.
+  static int fixed = -1;
+  if (fixed < 0) { const char* e = getenv("APH_SAMPLE_BWD_FIXED"); fixed = (e && e[0] == '1') ? 1 : 0; }
+  if (fixed) k_sample_bwd<<<S * 3, 1024, smem, (cudaStream_t)stream>>>(grad_out, H, W, pad_top, pad_left, table, size, kind, grad_canvas);
+  else k_sample_bwd_cas<<<S * 3, 1024, smem, (cudaStream_t)stream>>>(grad_out, H, W, pad_top, pad_left, table, size, kind, grad_canvas);
   APH_LAUNCH_OK();
   return 0;
 }

@@ -354,109 +354,241 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int q = warp & 3, half = (warp - 4) >> 2;      // half = column group 0..3 of this warp
     const uint32_t stage = smem_u32(smem + L::EPI_OFFSET + (warp - 4) * (32 * 128));
     const int c4 = lane & 7, rsub = lane >> 3;
-    uint32_t tile_iter = 0;
-    WorkIter wi; wi.init(epi.sk, tile0, tile_step, num_tiles, k_blocks);
-    int tile, kb0, kb1;
-    for (; wi.next(tile, kb0, kb1); ++tile_iter) {
-      const int m_blk = (tile / n_tiles) * CG + (int)rank, n_blk = tile % n_tiles;
-      const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
-      // stream-K roles of this item: park the partial (tile continues from another group's k-blocks) or fix it up
-      const bool p_store = epi.sk && kb0 > 0, p_fix = epi.sk && kb1 < k_blocks;
-      float* ws_st = epi.sk_ws + ((size_t)(tile0 * CG + (int)rank) * GEMM_BM) * BN;             // slot of this group
-      const float* ws_fx = epi.sk_ws + ((size_t)((tile0 + 1) * CG + (int)rank) * GEMM_BM) * BN;  // slot of the next group
-      if (p_fix) {
-        if (lane == 0) { volatile int* f = epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4); const long long t0 = clock64(); while (*f == 0 && clock64() - t0 < 4000000000LL) { } }   /* bounded (~2 s): a protocol bug must fail a test, not hang the GPU */
-        __threadfence();
-        __syncwarp();
-      }
-      mbar_wait(&tfull_bar[as], aph_);
-      tc_fence_after();
-      const int m_base = m_blk * GEMM_BM + q * 32;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += GEMM_EPI_WARPS / 4) {
-        // global operands of the fused epilogue are fetched FIRST (8 independent loads in flight per lane): issued inside
-        // the store loop they serialise behind the stores (possible aliasing) and the epilogue becomes load-latency bound
-        const int col = n_blk * BN + c * 32 + 4 * c4;
-        const size_t off0 = (size_t)(m_base + rsub) * shp.N + col;
-        const size_t step = (size_t)4 * shp.N;
-        float4 res4[EPI == EPI_BIAS_RESID ? 8 : 1];
-        uint2 gin[EPI == EPI_GELUGRAD_BF16 ? 8 : 1];
-        if ((EPI == EPI_BIAS_RESID || EPI == EPI_GELUGRAD_BF16) && !p_store) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const bool ok = m_base + it * 4 + rsub < shp.M;
-            if (EPI == EPI_BIAS_RESID) res4[it] = ok ? __ldg(reinterpret_cast<const float4*>(epi.resid + off0 + it * step)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (EPI == EPI_GELUGRAD_BF16) gin[it] = ok ? __ldg(reinterpret_cast<const uint2*>(epi.gelu_in + off0 + it * step)) : make_uint2(0u, 0u);
-          }
-        }
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_wait_ld();
-        if (c + GEMM_EPI_WARPS / 4 >= BN / 32) {          // this warp's last read of the accumulator: hand the TMEM stage back
-          tc_fence_before();
+    // Two loop forms. The gelu-grad kind software-pipelines its global operand (the saved pre-activation) one chunk ahead in a
+    // second 16-register buffer; the other kinds keep the single-chunk loop (pipelining the 32-register residual operand, or
+    // merely restructuring the operand-free kinds, measured slower in r1p).
+    if constexpr (EPI == EPI_GELUGRAD_BF16) {
+      uint32_t tile_iter = 0;
+      WorkIter wi; wi.init(epi.sk, tile0, tile_step, num_tiles, k_blocks);
+      // Global operands of the fused epilogue (the fp32 residual / the saved pre-activation) are software-pipelined one 32-column
+      // chunk ahead, across tile boundaries as well: fetched right before use they cost a full HBM round trip per chunk (ncu r1l:
+      // 28 % of the gelu-grad kernel's stall samples sat on the first use of these registers).
+      constexpr int CSTEP = GEMM_EPI_WARPS / 4, NCH = (BN / 32) / CSTEP;          // chunks per warp per tile (even)
+      constexpr int CU = 2;
+      static_assert(NCH % 2 == 0, "the operand double buffer assumes an even chunk count");
+      float4 res4[2][EPI == EPI_BIAS_RESID ? 8 : 1];
+      uint2 gin[2][EPI == EPI_GELUGRAD_BF16 ? 8 : 1];
+  #define APH_FETCH_OPS(TILE_, C_, BUF_)                                                                                          \
+      do {                                                                                                                        \
+        const int fm_ = ((TILE_) / n_tiles * CG + (int)rank) * GEMM_BM + q * 32;                                                  \
+        const size_t fo_ = (size_t)(fm_ + rsub) * shp.N + ((TILE_) % n_tiles) * BN + (C_) * 32 + 4 * c4;                          \
+        _Pragma("unroll")                                                                                                         \
+        for (int it = 0; it < 8; ++it) {                                                                                          \
+          const bool ok = fm_ + it * 4 + rsub < shp.M;                                                                            \
+          if (EPI == EPI_BIAS_RESID) res4[BUF_][it] = ok ? __ldg(reinterpret_cast<const float4*>(epi.resid + fo_ + (size_t)it * 4 * shp.N)) : make_float4(0.f, 0.f, 0.f, 0.f); \
+          if (EPI == EPI_GELUGRAD_BF16) gin[BUF_][it] = ok ? __ldg(reinterpret_cast<const uint2*>(epi.gelu_in + fo_ + (size_t)it * 4 * shp.N)) : make_uint2(0u, 0u); \
+        }                                                                                                                         \
+      } while (0)
+      int tile, kb0, kb1;
+      bool have = wi.next(tile, kb0, kb1);
+      if (have && !(epi.sk && kb0 > 0)) APH_FETCH_OPS(tile, half, 0);
+      while (have) {
+        int ntile = 0, nkb0 = 0, nkb1 = 0;
+        const bool have_n = wi.next(ntile, nkb0, nkb1);
+        const int m_blk = (tile / n_tiles) * CG + (int)rank, n_blk = tile % n_tiles;
+        const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
+        // stream-K roles of this item: park the partial (tile continues from another group's k-blocks) or fix it up
+        const bool p_store = epi.sk && kb0 > 0, p_fix = epi.sk && kb1 < k_blocks;
+        float* ws_st = epi.sk_ws + ((size_t)(tile0 * CG + (int)rank) * GEMM_BM) * BN;             // slot of this group
+        const float* ws_fx = epi.sk_ws + ((size_t)((tile0 + 1) * CG + (int)rank) * GEMM_BM) * BN;  // slot of the next group
+        if (p_fix) {
+          if (lane == 0) { volatile int* f = epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4); const long long t0 = clock64(); while (*f == 0 && clock64() - t0 < 4000000000LL) { } }   /* bounded (~2 s): a protocol bug must fail a test, not hang the GPU */
+          __threadfence();
           __syncwarp();
-          if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0)); else mbar_arrive(&tempty_bar[as]); }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)      // lane = row: write its 32 columns as 8 swizzled 16-byte chunks
-          sts128(stage + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-        __syncwarp();
-        size_t off = off0;
-#pragma unroll
-        for (int it = 0; it < 8; ++it, off += step) {
-          const int rr = it * 4 + rsub;
-          const int m = m_base + rr;
-          if (m >= shp.M) break;
-          float4 v = lds128(stage + rr * 128 + ((c4 ^ (rr & 7)) << 4));
-          if (p_store || p_fix) {
-            const size_t woff = (size_t)(q * 32 + rr) * BN + c * 32 + 4 * c4;
-            if (p_store) { *reinterpret_cast<float4*>(ws_st + woff) = v; continue; }
-            const float4 w = __ldcg(reinterpret_cast<const float4*>(ws_fx + woff));
-            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        mbar_wait(&tfull_bar[as], aph_);
+        tc_fence_after();
+        const int m_base = m_blk * GEMM_BM + q * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+  #pragma unroll 1
+        for (int ci0 = 0; ci0 < NCH; ci0 += CU) {
+  #pragma unroll
+        for (int cu = 0; cu < CU; ++cu) {                  // pairs of chunks: the operand buffer index is a compile-time constant
+          const int ci = ci0 + cu;
+          const int c = half + ci * CSTEP;
+          // next chunk's (or the next tile's first chunk's) operands
+          if (ci + 1 < NCH) { if (!p_store) APH_FETCH_OPS(tile, c + CSTEP, (cu + 1) & 1); }
+          else if (have_n && !(epi.sk && nkb0 > 0)) APH_FETCH_OPS(ntile, half, (cu + 1) & 1);
+          const int col = n_blk * BN + c * 32 + 4 * c4;
+          const size_t off0 = (size_t)(m_base + rsub) * shp.N + col;
+          const size_t step = (size_t)4 * shp.N;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_wait_ld();
+          if (ci == NCH - 1) {                             // this warp's last read of the accumulator: hand the TMEM stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0)); else mbar_arrive(&tempty_bar[as]); }
           }
-          if (EPI == EPI_F32) {
-            if (epi.nostore) { if (v.x == 1.2345e30f) epi.out_f32[0] = v.y; continue; }
-            *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
-          } else if (EPI == EPI_UNPATCH) {
-            const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
-            const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
-            const int ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
-            *reinterpret_cast<float4*>(epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px) = v;
-          } else if (EPI == EPI_BIAS_RESID) {
-            const float4 b = res4[EPI == EPI_BIAS_RESID ? it : 0];
-            v.x += bias4.x + b.x; v.y += bias4.y + b.y; v.z += bias4.z + b.z; v.w += bias4.w + b.w;
-            *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
-          } else {
-            if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
-            if (EPI == EPI_BIAS_GELU) {
+  #pragma unroll
+          for (int i = 0; i < 8; ++i)      // lane = row: write its 32 columns as 8 swizzled 16-byte chunks
+            sts128(stage + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          __syncwarp();
+          size_t off = off0;
+  #pragma unroll
+          for (int it = 0; it < 8; ++it, off += step) {
+            const int rr = it * 4 + rsub;
+            const int m = m_base + rr;
+            if (m >= shp.M) break;
+            float4 v = lds128(stage + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+            if (p_store || p_fix) {
+              const size_t woff = (size_t)(q * 32 + rr) * BN + c * 32 + 4 * c4;
+              if (p_store) { *reinterpret_cast<float4*>(ws_st + woff) = v; continue; }
+              const float4 w = __ldcg(reinterpret_cast<const float4*>(ws_fx + woff));
+              v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+            }
+            if (EPI == EPI_F32) {
+              if (epi.nostore) { if (v.x == 1.2345e30f) epi.out_f32[0] = v.y; continue; }
+              *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
+            } else if (EPI == EPI_UNPATCH) {
+              const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
+              const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
+              const int ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
+              *reinterpret_cast<float4*>(epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px) = v;
+            } else if (EPI == EPI_BIAS_RESID) {
+              const float4 b = res4[cu][EPI == EPI_BIAS_RESID ? it : 0];
+              v.x += bias4.x + b.x; v.y += bias4.y + b.y; v.z += bias4.z + b.z; v.w += bias4.w + b.w;
+              *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
+            } else {
+              if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+              if (EPI == EPI_BIAS_GELU) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+                uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+                *reinterpret_cast<uint2*>(epi.out_pre + off) = u;
+                v.x = quickgelu(v.x); v.y = quickgelu(v.y); v.z = quickgelu(v.z); v.w = quickgelu(v.w);
+              }
+              if (EPI == EPI_GELUGRAD_BF16) {
+                const uint2 u = gin[cu][EPI == EPI_GELUGRAD_BF16 ? it : 0];
+                const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+                const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+                v.x *= quickgelu_grad(h0.x); v.y *= quickgelu_grad(h0.y); v.z *= quickgelu_grad(h1.x); v.w *= quickgelu_grad(h1.y);
+              }
               __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
               uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-              *reinterpret_cast<uint2*>(epi.out_pre + off) = u;
-              v.x = quickgelu(v.x); v.y = quickgelu(v.y); v.z = quickgelu(v.z); v.w = quickgelu(v.w);
+              *reinterpret_cast<uint2*>(epi.out_bf16 + off) = u;
             }
-            if (EPI == EPI_GELUGRAD_BF16) {
-              const uint2 u = gin[EPI == EPI_GELUGRAD_BF16 ? it : 0];
-              const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-              const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-              v.x *= quickgelu_grad(h0.x); v.y *= quickgelu_grad(h0.y); v.z *= quickgelu_grad(h1.x); v.w *= quickgelu_grad(h1.y);
-            }
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-            uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(epi.out_bf16 + off) = u;
           }
+          __syncwarp();                    // staging tile is reused by this warp's next chunk
         }
-        __syncwarp();                    // staging tile is reused by this warp's next chunk
+        }
+        if (p_store) {                     // publish this warp's part of the parked partial
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + (tile0 * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 1;
+        } else if (p_fix) {                // consumed: re-arm the flag for the next launch
+          __syncwarp();
+          if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 0;
+        }
+        tile = ntile; kb0 = nkb0; kb1 = nkb1; have = have_n; ++tile_iter;
       }
-      if (p_store) {                     // publish this warp's part of the parked partial
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + (tile0 * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 1;
-      } else if (p_fix) {                // consumed: re-arm the flag for the next launch
-        __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 0;
+  #undef APH_FETCH_OPS
+    } else {
+      uint32_t tile_iter = 0;
+      WorkIter wi; wi.init(epi.sk, tile0, tile_step, num_tiles, k_blocks);
+      int tile, kb0, kb1;
+      for (; wi.next(tile, kb0, kb1); ++tile_iter) {
+        const int m_blk = (tile / n_tiles) * CG + (int)rank, n_blk = tile % n_tiles;
+        const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
+        // stream-K roles of this item: park the partial (tile continues from another group's k-blocks) or fix it up
+        const bool p_store = epi.sk && kb0 > 0, p_fix = epi.sk && kb1 < k_blocks;
+        float* ws_st = epi.sk_ws + ((size_t)(tile0 * CG + (int)rank) * GEMM_BM) * BN;             // slot of this group
+        const float* ws_fx = epi.sk_ws + ((size_t)((tile0 + 1) * CG + (int)rank) * GEMM_BM) * BN;  // slot of the next group
+        if (p_fix) {
+          if (lane == 0) { volatile int* f = epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4); const long long t0 = clock64(); while (*f == 0 && clock64() - t0 < 4000000000LL) { } }   /* bounded (~2 s): a protocol bug must fail a test, not hang the GPU */
+          __threadfence();
+          __syncwarp();
+        }
+        mbar_wait(&tfull_bar[as], aph_);
+        tc_fence_after();
+        const int m_base = m_blk * GEMM_BM + q * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+  #pragma unroll 1
+        for (int c = half; c < BN / 32; c += GEMM_EPI_WARPS / 4) {
+          // global operands of the fused epilogue are fetched FIRST (8 independent loads in flight per lane): issued inside
+          // the store loop they serialise behind the stores (possible aliasing) and the epilogue becomes load-latency bound
+          const int col = n_blk * BN + c * 32 + 4 * c4;
+          const size_t off0 = (size_t)(m_base + rsub) * shp.N + col;
+          const size_t step = (size_t)4 * shp.N;
+          float4 res4[EPI == EPI_BIAS_RESID ? 8 : 1];
+          uint2 gin[EPI == EPI_GELUGRAD_BF16 ? 8 : 1];
+          if ((EPI == EPI_BIAS_RESID || EPI == EPI_GELUGRAD_BF16) && !p_store) {
+  #pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const bool ok = m_base + it * 4 + rsub < shp.M;
+              if (EPI == EPI_BIAS_RESID) res4[it] = ok ? __ldg(reinterpret_cast<const float4*>(epi.resid + off0 + it * step)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (EPI == EPI_GELUGRAD_BF16) gin[it] = ok ? __ldg(reinterpret_cast<const uint2*>(epi.gelu_in + off0 + it * step)) : make_uint2(0u, 0u);
+            }
+          }
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_wait_ld();
+          if (c + GEMM_EPI_WARPS / 4 >= BN / 32) {          // this warp's last read of the accumulator: hand the TMEM stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0)); else mbar_arrive(&tempty_bar[as]); }
+          }
+  #pragma unroll
+          for (int i = 0; i < 8; ++i)      // lane = row: write its 32 columns as 8 swizzled 16-byte chunks
+            sts128(stage + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          __syncwarp();
+          size_t off = off0;
+  #pragma unroll
+          for (int it = 0; it < 8; ++it, off += step) {
+            const int rr = it * 4 + rsub;
+            const int m = m_base + rr;
+            if (m >= shp.M) break;
+            float4 v = lds128(stage + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+            if (p_store || p_fix) {
+              const size_t woff = (size_t)(q * 32 + rr) * BN + c * 32 + 4 * c4;
+              if (p_store) { *reinterpret_cast<float4*>(ws_st + woff) = v; continue; }
+              const float4 w = __ldcg(reinterpret_cast<const float4*>(ws_fx + woff));
+              v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+            }
+            if (EPI == EPI_F32) {
+              if (epi.nostore) { if (v.x == 1.2345e30f) epi.out_f32[0] = v.y; continue; }
+              *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
+            } else if (EPI == EPI_UNPATCH) {
+              const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
+              const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
+              const int ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
+              *reinterpret_cast<float4*>(epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px) = v;
+            } else if (EPI == EPI_BIAS_RESID) {
+              const float4 b = res4[EPI == EPI_BIAS_RESID ? it : 0];
+              v.x += bias4.x + b.x; v.y += bias4.y + b.y; v.z += bias4.z + b.z; v.w += bias4.w + b.w;
+              *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
+            } else {
+              if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+              if (EPI == EPI_BIAS_GELU) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+                uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+                *reinterpret_cast<uint2*>(epi.out_pre + off) = u;
+                v.x = quickgelu(v.x); v.y = quickgelu(v.y); v.z = quickgelu(v.z); v.w = quickgelu(v.w);
+              }
+              if (EPI == EPI_GELUGRAD_BF16) {
+                const uint2 u = gin[EPI == EPI_GELUGRAD_BF16 ? it : 0];
+                const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+                const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+                v.x *= quickgelu_grad(h0.x); v.y *= quickgelu_grad(h0.y); v.z *= quickgelu_grad(h1.x); v.w *= quickgelu_grad(h1.y);
+              }
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+              uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+              *reinterpret_cast<uint2*>(epi.out_bf16 + off) = u;
+            }
+          }
+          __syncwarp();                    // staging tile is reused by this warp's next chunk
+        }
+        if (p_store) {                     // publish this warp's part of the parked partial
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + (tile0 * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 1;
+        } else if (p_fix) {                // consumed: re-arm the flag for the next launch
+          __syncwarp();
+          if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 0;
+        }
       }
     }
   }

@@ -112,7 +112,7 @@ int aph_valid_rgb_bwd(const float* grad_out, const float* out, int64_t hw, const
  * (bilinear, zeros, x coverage) -> erase -> rotate (bilinear, zeros, x coverage) -> normalise.
  * canvas [3,H,W]; the sampling frame is the canvas wrap-padded by (pad_top, pad_left)
  * ('over*' aligns, utils.py:152-187; 0,0 otherwise); table: DEVICE [S, APH_CROP_PARAM_FLOATS];
- * out [S,3,size,size]. size*size*4 bytes must fit one CTA's shared memory (size <= 231).           */
+ * out [S,3,size,size]. the resized crop, its tap tables and the per-warp strips must fit one CTA's shared memory (size <= 224).           */
 int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, int pad_left,
                    const float* table, int S, int size, int kind, float* out, void* stream);
 /* grad_out [S,3,size,size] -> grad_canvas [3,H,W] (zeroed here, then accumulated).                 */

@@ -122,8 +122,10 @@ def test_sampler_vs_reference_golden(L, golden, name):
     assert _rel(canvas.grad[:, :, ::st, ::st], golden['smp_%s_gcanvas' % name]) < 1e-4
 
 
-def test_sampler_backward_gather_path_matches_scatter(L):
-    """The opt-in atomic-free backward (APH_SAMPLE_BWD_GATHER=1, separate process) equals the default scatter path."""
+def test_sampler_backward_variants_agree(L):
+    """Backward variants (each in its own process): default = fp32 compare-and-swap shared accumulation; APH_SAMPLE_BWD_FIXED=1 =
+    integer fixed-point shared accumulation; APH_SAMPLE_BWD_GATHER=1 = atomic-free gather. All must agree to fp32 round-off, also
+    for gradients 1e-6 in magnitude (the fixed-point scale is per crop, not absolute)."""
     import os, subprocess, sys
     code = """
 import torch, numpy as np, sys
@@ -135,16 +137,16 @@ c = torch.rand(1, 3, 360, 640).cuda().requires_grad_(True)
 torch.manual_seed(5); np.random.seed(5)
 out = slice_imgs([c], 24, 224, transforms.transforms_fast, 'uniform', 0.4)[0]
 torch.manual_seed(6)
-(out * torch.randn(out.shape).cuda()).sum().backward()
+(out * (torch.randn(out.shape) * float(sys.argv[2])).cuda()).sum().backward()
 torch.save(c.grad.cpu(), sys.argv[1])
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for flag in ('0', '1'):
-        path = '/tmp/aph_gather_%s.pt' % flag
-        env = dict(os.environ, APH_SAMPLE_BWD_GATHER=flag)
-        subprocess.check_call([sys.executable, '-c', code, path], env=env)
-        outs.append(torch.load(path))
-    assert _rel(outs[1], outs[0]) < 1e-5
+    for mag in ('1.0', '1e-6'):
+        outs = []
+        for k, env_add in enumerate((dict(APH_SAMPLE_BWD_FIXED='1'), dict(), dict(APH_SAMPLE_BWD_GATHER='1'))):
+            path = '/tmp/aph_bwd_variant_%d.pt' % k
+            subprocess.check_call([sys.executable, '-c', code, path, mag], env=dict(os.environ, **env_add))
+            outs.append(torch.load(path))
+        assert _rel(outs[0], outs[1]) < 1e-5 and _rel(outs[2], outs[1]) < 1e-5
 
 
 @pytest.mark.parametrize('kind', [0, 1, 2])
