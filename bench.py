@@ -98,6 +98,8 @@ class DeviceStep:
         g = torch.Generator().manual_seed(1234)
         txt = torch.randn(1, 512, generator=g); self.txt = (10. * txt / txt.norm()).to(dev)
         lo, hi = _rng.shard_range(S_total, rank, world)
+        if world == 1 and os.environ.get('APH_BENCH_SHARD_OF'):
+            lo, hi = _rng.shard_range(S_total, 0, int(os.environ['APH_BENCH_SHARD_OF']))
         assert hi - lo == S_local
         tabs = []
         for _ in range(n_tables):       # every rank replays the full stream, keeps its shard (results independent of N)
@@ -270,6 +272,8 @@ def run_ours(args):
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
     from aphantasia_b200 import _lib, _rng
     lo, hi = _rng.shard_range(S_TOTAL, rank, world)
+    if world == 1 and os.environ.get('APH_BENCH_SHARD_OF'):      # profiling knob: one rank's shard of an N-GPU run on a single GPU (no all-reduce)
+        lo, hi = _rng.shard_range(S_TOTAL, 0, int(os.environ['APH_BENCH_SHARD_OF']))
     K, Wm = args.steps, args.warmup
 
     # ---- device-resident leg (value)
