@@ -111,6 +111,31 @@ def _frame(H, W, align):
     return (fh - H) // 2, (fw - W) // 2, fh, fw
 
 
+_NP_INPLACE = None     # (bit_generator, address of its mt19937_state) once verified; False if the layout check failed
+
+
+def _numpy_state_address():
+    """Address of the global legacy RandomState's `mt19937_state { uint32_t key[624]; int pos; }` (numpy/random/src/mt19937/
+    mt19937.h), so the native replay can continue NumPy's stream in place: np.random.get_state() + set_state() cost 88 us per
+    slice_imgs call, more than the replay itself. The layout is verified once against the public state; None -> copy path."""
+    global _NP_INPLACE
+    import ctypes as C
+    rs = np.random.mtrand._rand
+    if _NP_INPLACE is None:
+        try:
+            bg = rs._bit_generator
+            addr = int(bg.ctypes.state_address)
+            name, key, pos = np.random.get_state()[:3]
+            raw = np.frombuffer((C.c_uint32 * 625).from_address(addr), dtype=np.uint32)
+            ok = name == 'MT19937' and np.array_equal(raw[:624], np.asarray(key, dtype=np.uint32)) and int(raw[624]) == int(pos)
+            _NP_INPLACE = (bg, addr) if ok else False
+        except Exception:
+            _NP_INPLACE = False
+    if _NP_INPLACE and rs._bit_generator is _NP_INPLACE[0]:
+        return _NP_INPLACE[1]
+    return None
+
+
 def draw_crop_table_native(count, canvas_hw, size=224, kind=TF_FAST, align='uniform', macro=0., n_imgs=1):
     """Same draws as draw_crop_table_py, but the per-crop loop continues both Mersenne-Twister streams in C."""
     import ctypes as C
@@ -125,15 +150,21 @@ def draw_crop_table_native(count, canvas_hw, size=224, kind=TF_FAST, align='unif
         rnd_offy = torch.rand(count)
     pad_top, pad_left, fh, fw = _frame(H, W, align)
     tstate = torch.get_rng_state()
-    name, key, pos, has_gauss, cached = np.random.get_state()
-    key = np.ascontiguousarray(key, dtype=np.uint32)
-    cpos = C.c_int32(int(pos))
     tabs = np.empty((n_imgs, count, CROP_PARAM_FLOATS), dtype=np.float32)
-    check(lib().aph_rng_crop_tables(tstate.data_ptr(), tstate.numel(), key.ctypes.data, C.byref(cpos), rnd_size.data_ptr(), rnd_offx.data_ptr(),
+    addr = _numpy_state_address()
+    if addr is not None:                     # NumPy's key[] / pos are advanced where they live
+        key_ptr, pos_ptr, np_state = addr, C.cast(addr + 624 * 4, C.POINTER(C.c_int32)), None
+    else:
+        name, key, pos, has_gauss, cached = np.random.get_state()
+        key = np.ascontiguousarray(key, dtype=np.uint32)
+        cpos = C.c_int32(int(pos))
+        key_ptr, pos_ptr, np_state = key.ctypes.data, C.byref(cpos), (name, key, has_gauss, cached)
+    check(lib().aph_rng_crop_tables(tstate.data_ptr(), tstate.numel(), key_ptr, pos_ptr, rnd_size.data_ptr(), rnd_offx.data_ptr(),
                                     rnd_offy.data_ptr(), count, H, W, fh, fw, size, kind, float(macro), n_imgs, tabs.ctypes.data),
           'aph_rng_crop_tables')
     torch.set_rng_state(tstate)
-    np.random.set_state((name, key, int(cpos.value), has_gauss, cached))
+    if np_state is not None:
+        np.random.set_state((np_state[0], np_state[1], int(cpos.value), np_state[2], np_state[3]))
     return [tabs[i] for i in range(n_imgs)], (pad_top, pad_left, fh, fw)
 
 

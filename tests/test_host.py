@@ -135,3 +135,27 @@ def test_bench_reference_arm_prints_the_contract_line():
     cb = d['cpu_baseline']
     assert cb['kind'] in ('port', 'reference') and cb['cores'] >= 1 and cb['sample'] and cb['value'] == d['value']
     assert d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+
+
+def test_native_replay_in_place_numpy_state_equals_copy_path():
+    """The native replay advances NumPy's global MT19937 state where it lives (no get_state/set_state round trip); the result and
+    the state it leaves behind must equal the copy path's, also across reseeding and interleaved draws."""
+    from aphantasia_b200 import _rng
+
+    def run(force_copy):
+        torch.manual_seed(3); np.random.seed(3)
+        _rng._NP_INPLACE = False if force_copy else None
+        outs = []
+        for i in range(5):
+            tabs, _ = _rng.draw_crop_table_native(37, (360, 640), 224, _rng.TF_FAST, 'uniform', 0.4)
+            outs.append(tabs[0].copy())
+            outs.append(np.array([np.random.rand(), np.random.randint(0, 100), torch.rand(1).item(), np.random.randn()]))
+            if i == 2:
+                np.random.seed(10)
+        return outs
+    try:
+        a, b = run(False), run(True)
+    finally:
+        _rng._NP_INPLACE = None
+    assert _rng._numpy_state_address() is not None          # this NumPy exposes the expected mt19937_state layout
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
