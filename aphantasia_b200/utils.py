@@ -52,17 +52,30 @@ def _transform_kind(transform):
     return kind
 
 
-_pinned = {}
+_pinned = {}          # table shape -> ring of pinned staging buffers with the event of the copy that last read each
+_PIN_RING = 4
 
 
 def _table_to_device(tab, device):
-    """H2D of the per-step crop table through a reused pinned staging buffer (async on the current stream)."""
-    key = tab.shape
-    buf = _pinned.get(key)
-    if buf is None:
-        buf = _pinned[key] = torch.empty(tab.shape, dtype=torch.float32).pin_memory()
+    """H2D of the per-step crop table through reused pinned staging buffers (async on the current stream). A ring, because the
+    host may run a step ahead of the GPU (the script does not synchronise every step): a single buffer could be overwritten
+    with step k+1's table before the copy of step k has executed. A slot is reused only after its copy event has completed."""
+    key = tuple(tab.shape)
+    ring = _pinned.get(key)
+    if ring is None:
+        ring = _pinned[key] = {'bufs': [torch.empty(tab.shape, dtype=torch.float32).pin_memory() for _ in range(_PIN_RING)],
+                               'evs': [None] * _PIN_RING, 'next': 0}
+    i = ring['next']
+    ring['next'] = (i + 1) % _PIN_RING
+    if ring['evs'][i] is not None:
+        ring['evs'][i].synchronize()          # normally completed long ago
+    else:
+        ring['evs'][i] = torch.cuda.Event()
+    buf = ring['bufs'][i]
     buf.numpy()[...] = tab
-    return buf.to(device, non_blocking=True)
+    out = buf.to(device, non_blocking=True)
+    ring['evs'][i].record()
+    return out
 
 
 def slice_imgs(imgs, count, size=224, transform=None, align='uniform', macro=0.):
