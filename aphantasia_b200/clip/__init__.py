@@ -15,6 +15,7 @@ from collections import OrderedDict
 
 import torch
 
+from .. import _trace
 from .._lib import VitConfig, check, lib, require_cuda, stream_ptr
 
 _MODELS = {'ViT-B/32': dict(patch=32, width=768, layers=12, heads=12, out_dim=512, res=224),
@@ -68,14 +69,32 @@ class _EncodeImage(torch.autograd.Function):
         emb = torch.empty(S, vis.output_dim, device=xi.device, dtype=torch.float32)
         need_bwd = x.requires_grad
         check(lib().aph_vit_fwd(vis.handle, xi.data_ptr(), S, emb.data_ptr(), int(need_bwd), stream_ptr()), 'aph_vit_fwd')
+        _trace.encode()
         ctx.vis, ctx.S, ctx.shape = vis, S, tuple(xi.shape)
+        if need_bwd:
+            # The handle owns ONE activation arena: a later grad-tracked forward of the same model overwrites what this call
+            # saved (clip_fft.py --enforce runs encode_image twice before loss.backward(), :254 and :276). Each saving forward
+            # gets a generation stamp; a backward whose stamp is stale re-runs its forward from the saved input first
+            # (deterministic kernels: identical activations), instead of silently using the other call's activations.
+            vis._generation += 1
+            ctx.generation = vis._generation
+            ctx.handle_epoch = vis._handle_epoch
+            ctx.save_for_backward(xi)
         return emb
 
     @staticmethod
     def backward(ctx, g):
+        vis = ctx.vis
+        xi, = ctx.saved_tensors
         g = g.contiguous().float()
+        if ctx.generation != vis._generation or ctx.handle_epoch != vis._handle_epoch:
+            vis._ensure(ctx.S)
+            scratch = torch.empty(ctx.S, vis.output_dim, device=g.device, dtype=torch.float32)
+            check(lib().aph_vit_fwd(vis.handle, xi.data_ptr(), ctx.S, scratch.data_ptr(), 1, stream_ptr()), 'aph_vit_fwd (recompute)')
+            vis._generation += 1            # the arena now belongs to this call; any other pending backward must recompute too
+            vis.recomputes += 1
         gi = torch.empty(ctx.shape, device=g.device, dtype=torch.float32)
-        check(lib().aph_vit_bwd(ctx.vis.handle, g.data_ptr(), ctx.S, gi.data_ptr(), stream_ptr()), 'aph_vit_bwd')
+        check(lib().aph_vit_bwd(vis.handle, g.data_ptr(), ctx.S, gi.data_ptr(), stream_ptr()), 'aph_vit_bwd')
         return gi, None
 
 
@@ -93,6 +112,7 @@ class VisionTransformer:
         self.output_dim = sd['proj'].shape[1]
         self._sd = {k: v.detach().float().contiguous() for k, v in sd.items()}
         self.handle, self.max_batch = None, 0
+        self._generation, self.recomputes, self._handle_epoch = 0, 0, 0        # see _EncodeImage
         if max_batch:
             self._ensure(max_batch)
 
@@ -111,6 +131,7 @@ class VisionTransformer:
         torch.cuda.current_stream().synchronize()      # staging copies `d` die with this scope
         check(lib().aph_vit_finalize(h), 'aph_vit_finalize')
         self.handle, self.max_batch = h, int(S)
+        self._handle_epoch += 1
 
     def close(self):
         if self.handle is not None:

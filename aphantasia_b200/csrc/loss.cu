@@ -63,9 +63,111 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
   }
 }
 
+// ---- optional loss heads of the step -----------------------------------------------------------
+// derivat(img, mode='naiv') (/root/reference/aphantasia/utils.py:256-268, the only mode clip_fft.py:272 uses):
+//   0.5 * (mean |img[..., x+1] - img[..., x]| + mean |img[..., y+1, :] - img[..., y, :]|)
+// sums[0] / sums[1] accumulate the two absolute-difference sums in fp64; k_derivat_fin folds them into the value.
+__global__ void __launch_bounds__(256) k_derivat_fwd(const float* __restrict__ img, int C, int H, int W, double* __restrict__ sums) {
+  const size_t n = (size_t)C * H * W;
+  double sx = 0., sy = 0.;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const float v = img[i];
+    if (x + 1 < W) sx += fabsf(img[i + 1] - v);
+    if (y + 1 < H) sy += fabsf(img[i + W] - v);
+  }
+  sx = warp_sum_d(sx); sy = warp_sum_d(sy);
+  __shared__ double red[2][8];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][wid] = sx; red[1][wid] = sy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0., b = 0.;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; }
+    atomicAdd(&sums[0], a); atomicAdd(&sums[1], b);
+  }
+}
+__global__ void k_derivat_fin(const double* __restrict__ sums, double nx, double ny, float* __restrict__ value) {
+  *value = (float)(0.5 * (sums[0] / nx + sums[1] / ny));
+}
+__device__ __forceinline__ float sgnf(float d) { return (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f); }
+// d value / d img, times the upstream gradient (a DEVICE scalar: no host sync)
+__global__ void __launch_bounds__(256) k_derivat_bwd(const float* __restrict__ img, int C, int H, int W, const float* __restrict__ up,
+                                                     float inv_nx, float inv_ny, float* __restrict__ grad) {
+  const size_t n = (size_t)C * H * W;
+  const float g = 0.5f * up[0];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const float v = img[i];
+    float a = 0.f, b = 0.f;
+    if (x > 0) a += sgnf(v - img[i - 1]);
+    if (x + 1 < W) a -= sgnf(img[i + 1] - v);
+    if (y > 0) b += sgnf(v - img[i - W]);
+    if (y + 1 < H) b -= sgnf(img[i + W] - v);
+    grad[i] = g * (a * inv_nx + b * inv_ny);
+  }
+}
+
+// Linear head on the embeddings (the LAION aesthetic predictor of --aest is nn.Linear(512, 1), utils.py:402-413; clip_fft.py:255-256):
+// out[s] = <emb_s, w> + b; one warp per sample.
+__global__ void __launch_bounds__(256) k_head_fwd(const float* __restrict__ emb, int S, int D, const float* __restrict__ w,
+                                                  const float* __restrict__ b, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= S) return;
+  const float* e = emb + (size_t)warp * D;
+  float acc = 0.f;
+  for (int i = lane; i < D; i += 32) acc += e[i] * w[i];
+  acc = warp_sum(acc);
+  if (lane == 0) out[warp] = acc + (b ? b[0] : 0.f);
+}
+__global__ void __launch_bounds__(256) k_head_bwd(const float* __restrict__ g, const float* __restrict__ w, int S, int D, float* __restrict__ grad_emb) {
+  const size_t n = (size_t)S * D;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    grad_emb[i] = g[i / D] * w[i % D];
+}
+
 }  // namespace aph
 
 using namespace aph;
+
+extern "C" int aph_derivat_fwd(const float* img, int C, int H, int W, double* sums, float* value, void* stream) {
+  APH_REQUIRE(img && sums && value && C > 0 && H > 1 && W > 1, "aph_derivat_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  APH_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
+  const size_t n = (size_t)C * H * W;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8);
+  k_derivat_fwd<<<blocks, 256, 0, st>>>(img, C, H, W, sums);
+  APH_LAUNCH_OK();
+  k_derivat_fin<<<1, 1, 0, st>>>(sums, (double)C * H * (W - 1), (double)C * (H - 1) * W, value);
+  APH_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int aph_derivat_bwd(const float* img, int C, int H, int W, const float* upstream, float* grad_img, void* stream) {
+  APH_REQUIRE(img && upstream && grad_img && C > 0 && H > 1 && W > 1, "aph_derivat_bwd: bad arguments");
+  const size_t n = (size_t)C * H * W;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8);
+  k_derivat_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(img, C, H, W, upstream, (float)(1.0 / ((double)C * H * (W - 1))),
+                                                         (float)(1.0 / ((double)C * (H - 1) * W)), grad_img);
+  APH_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int aph_head_fwd(const float* emb, int S, int D, const float* w, const float* b, float* out, void* stream) {
+  APH_REQUIRE(emb && w && out && S > 0 && D > 0, "aph_head_fwd: bad arguments");
+  k_head_fwd<<<(S * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(emb, S, D, w, b, out);
+  APH_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int aph_head_bwd(const float* grad_out, const float* w, int S, int D, float* grad_emb, void* stream) {
+  APH_REQUIRE(grad_out && w && grad_emb && S > 0 && D > 0, "aph_head_bwd: bad arguments");
+  const size_t n = (size_t)S * D;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8);
+  k_head_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, w, S, D, grad_emb);
+  APH_LAUNCH_OK();
+  return 0;
+}
 
 extern "C" int aph_sim_fwd(const float* v1, int n1, const float* v2, int S, int D, int kind, float* value, float* grad_v1,
                            float* grad_v2, void* stream) {

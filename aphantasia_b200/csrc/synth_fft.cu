@@ -133,11 +133,22 @@ __device__ float2* fft_lines(float2* a, float2* b, const float2* tw, int N, cons
 
 // ---------------------------------------------------------------------------------------------
 // Column pass. FWD: in = params [3][H][Wh] complex (+scale, +shift), out = T. !FWD: in = dT, out = dP*scale.
+// Adam state for the fused update (row f2 of SURVEY 8f): the backward's last pass already holds dP = scale * dZ in registers,
+// so p / m / v are updated right there instead of writing dP, re-reading it in torch.optim.Adam's ~12 launches.
+struct AdamArgs { float2* p; float2* m; float2* v; float step_size, b1, b2, eps, inv_sqrt_bc2; int on; };
+
+__device__ __forceinline__ float adam_elem(float& p, float& m, float& v, float g, const AdamArgs& a) {
+  m = a.b1 * m + (1.f - a.b1) * g;
+  v = a.b2 * v + (1.f - a.b2) * g * g;
+  p -= a.step_size * m / (sqrtf(v) * a.inv_sqrt_bc2 + a.eps);
+  return p;
+}
+
 template <bool FWD>
 __global__ void __launch_bounds__(256) k_col_fft(const float2* __restrict__ in, float2* __restrict__ out,
                                                  const float* __restrict__ scale, const float* __restrict__ shift,
                                                  int shift_mode, const float2* __restrict__ twg, int H, int Wh, int C,
-                                                 Radices rad) {
+                                                 Radices rad, AdamArgs adam) {
   extern __shared__ float2 smem[];
   const int LS = H + 1;
   float2* tw = smem;                 // [H]
@@ -171,8 +182,15 @@ __global__ void __launch_bounds__(256) k_col_fft(const float2* __restrict__ in, 
     if (c < cols) {
       const size_t g = (size_t)n1 * Wh + k2base + c;
       float2 v = res[c * LS + n1];
-      if (!FWD) { const float s = scale[g]; v.x *= s; v.y *= s; }
-      out[ch * plane + g] = v;
+      if (!FWD) {
+        const float s = scale[g]; v.x *= s; v.y *= s;
+        if (adam.on) {
+          float2 pp = adam.p[ch * plane + g], mm = adam.m[ch * plane + g], vv = adam.v[ch * plane + g];
+          adam_elem(pp.x, mm.x, vv.x, v.x, adam); adam_elem(pp.y, mm.y, vv.y, v.y, adam);
+          adam.p[ch * plane + g] = pp; adam.m[ch * plane + g] = mm; adam.v[ch * plane + g] = vv;
+        }
+      }
+      if (out) out[ch * plane + g] = v;
     }
   }
 }
@@ -340,7 +358,7 @@ extern "C" int aph_synth_fft_fwd(aph_fft_plan* plan, const float* params, const 
   APH_CUDA_OK(cudaMemsetAsync(stats, 0, 4 * sizeof(double), st));
   const int col_tiles = (Wh + p->colC - 1) / p->colC;
   k_col_fft<true><<<3 * col_tiles, 256, p->smem_col, st>>>(reinterpret_cast<const float2*>(params), p->T, scale, shift,
-                                                          shift_mode, p->twH, H, Wh, p->colC, p->rh);
+                                                          shift_mode, p->twH, H, Wh, p->colC, p->rh, AdamArgs{});
   APH_LAUNCH_OK();
   const int groups = ((H + 1) / 2 + p->rowP - 1) / p->rowP;
   const float norm = (float)(1.0 / sqrt((double)H * W));
@@ -353,10 +371,10 @@ extern "C" int aph_synth_fft_fwd(aph_fft_plan* plan, const float* params, const 
   return 0;
 }
 
-extern "C" int aph_synth_fft_bwd(aph_fft_plan* plan, const float* grad_out, const float* out, const float* x_raw,
-                                 double* stats, const float* scale, float contrast, const float* colmat_host,
-                                 int apply_sigmoid, float* grad_params, void* stream) {
-  APH_REQUIRE(plan && grad_out && x_raw && stats && scale && grad_params, "aph_synth_fft_bwd: null pointer");
+static int synth_fft_bwd_impl(aph_fft_plan* plan, const float* grad_out, const float* out, const float* x_raw,
+                              double* stats, const float* scale, float contrast, const float* colmat_host,
+                              int apply_sigmoid, float* grad_params, const AdamArgs& adam, void* stream) {
+  APH_REQUIRE(plan && grad_out && x_raw && stats && scale && (grad_params || adam.on), "aph_synth_fft_bwd: null pointer");
   APH_REQUIRE(!apply_sigmoid || out, "aph_synth_fft_bwd: sigmoid backward needs the saved output");
   FftPlanImpl* p = reinterpret_cast<FftPlanImpl*>(plan);
   cudaStream_t st = (cudaStream_t)stream;
@@ -372,9 +390,27 @@ extern "C" int aph_synth_fft_bwd(aph_fft_plan* plan, const float* grad_out, cons
   APH_LAUNCH_OK();
   const int col_tiles = (Wh + p->colC - 1) / p->colC;
   k_col_fft<false><<<3 * col_tiles, 256, p->smem_col, st>>>(p->T, reinterpret_cast<float2*>(grad_params), scale, nullptr, 0,
-                                                           p->twH, H, Wh, p->colC, p->rh);
+                                                           p->twH, H, Wh, p->colC, p->rh, adam);
   APH_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int aph_synth_fft_bwd(aph_fft_plan* plan, const float* grad_out, const float* out, const float* x_raw,
+                                 double* stats, const float* scale, float contrast, const float* colmat_host,
+                                 int apply_sigmoid, float* grad_params, void* stream) {
+  return synth_fft_bwd_impl(plan, grad_out, out, x_raw, stats, scale, contrast, colmat_host, apply_sigmoid, grad_params, AdamArgs{}, stream);
+}
+
+extern "C" int aph_synth_fft_bwd_adam(aph_fft_plan* plan, const float* grad_out, const float* out, const float* x_raw,
+                                      double* stats, const float* scale, float contrast, const float* colmat_host,
+                                      int apply_sigmoid, float* grad_params, float* params, float* m, float* v,
+                                      float lr, float b1, float b2, float eps, int step, void* stream) {
+  APH_REQUIRE(params && m && v && step >= 1, "aph_synth_fft_bwd_adam: bad Adam state");
+  const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+  AdamArgs a;
+  a.p = reinterpret_cast<float2*>(params); a.m = reinterpret_cast<float2*>(m); a.v = reinterpret_cast<float2*>(v);
+  a.step_size = (float)(lr / bc1); a.b1 = b1; a.b2 = b2; a.eps = eps; a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2)); a.on = 1;
+  return synth_fft_bwd_impl(plan, grad_out, out, x_raw, stats, scale, contrast, colmat_host, apply_sigmoid, grad_params, a, stream);
 }
 
 namespace aph {

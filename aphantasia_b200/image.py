@@ -61,6 +61,17 @@ class _SynthFFT(torch.autograd.Function):
         x_raw, stats, out = ctx.saved_tensors
         gen = ctx.gen
         g = grad_out.contiguous().float()
+        fo = gen.fused_opt
+        opt = fo[0]() if (fo is not None and gen.pending_fwd == 1) else None
+        if opt is not None:
+            # row f2: exactly one grad-tracked synthesis since the last optimizer.step() -> this backward IS the whole gradient of
+            # the spectrum; Adam runs in the last FFT pass (dP never leaves registers) and step() finds nothing left to do
+            m, v, lr, b1, b2, eps, step = opt._fused_args(fo[1], fo[2])
+            p = gen.params
+            check(lib().aph_synth_fft_bwd_adam(gen.plan, g.data_ptr(), out.data_ptr(), x_raw.data_ptr(), stats.data_ptr(), gen.scale.data_ptr(),
+                                               ctx.contrast, ctx.colmat, ctx.sigmoid, None, p.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                               lr, b1, b2, eps, step, stream_ptr()), 'aph_synth_fft_bwd_adam')
+            return None, None, None, None, None, None
         gp = torch.empty(1, 3, gen.h, gen.wh, 2, device=g.device, dtype=torch.float32)
         check(lib().aph_synth_fft_bwd(gen.plan, g.data_ptr(), out.data_ptr(), x_raw.data_ptr(), stats.data_ptr(), gen.scale.data_ptr(),
                                       ctx.contrast, ctx.colmat, ctx.sigmoid, gp.data_ptr(), stream_ptr()), 'aph_synth_fft_bwd')
@@ -79,6 +90,9 @@ class FFTImage:
         plan = C.c_void_p()
         check(lib().aph_fft_plan_create(C.byref(plan), h, w), 'aph_fft_plan_create')
         self.plan = plan
+        self.fused_opt, self.pending_fwd = None, 0          # aphantasia_b200.optim.Adam hooks in here (row f2)
+        from .optim import register_generator
+        register_generator(params, self)
 
     def __del__(self):
         try:
@@ -88,6 +102,8 @@ class FFTImage:
             pass
 
     def fused(self, shift, contrast, colmat, sigmoid):
+        if torch.is_grad_enabled() and self.params.requires_grad:
+            self.pending_fwd += 1
         return _SynthFFT.apply(self.params, self, shift, contrast, colmat, sigmoid)
 
     def __call__(self, shift=None, contrast=1., *noargs, **nokwargs):

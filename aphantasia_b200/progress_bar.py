@@ -33,7 +33,12 @@ class ProgressBar(object):
         else:
             line = '\rcompleted %d, time %ds, %.1f steps/s' % (self.completed, int(elapsed + 0.5), 1. / rate)
         sys.stdout.write(line)
-        if self.completed == self.task_num: sys.stdout.write('\n')
+        if self.completed == self.task_num:
+            sys.stdout.write('\n')
+            # last preview frame submitted: wait for the asynchronous JPEG encoder before the caller reads the output
+            # directory (clip_fft.py:311-313 runs ffmpeg and img_list right after the loop)
+            from .utils import _drain_saves
+            _drain_saves()
         sys.stdout.flush()
         return self.completed
 

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import _dist, _rng
+from . import _dist, _rng, _trace
 from ._lib import check, lib, require_cuda, stream_ptr
 
 
@@ -100,21 +100,20 @@ def slice_imgs(imgs, count, size=224, transform=None, align='uniform', macro=0.)
 
 
 def apply_transform_standalone(x, transform):
-    """transform(x) outside slice_imgs: every image of the batch is an identity crop (csize == size)."""
+    """transform(x) outside slice_imgs: every image of the batch is an identity crop (csize == size). As in the reference
+    (torchvision draws get_params ONCE per call, transforms.py:165-170), one parameter row is drawn per call and applied to
+    every image of the batch."""
     require_cuda(x, 'transform input')
     n, c, h, w = x.shape
     assert c == 3 and h == w, 'fused transforms expect [N,3,s,s]'
-    outs = []
-    for i in range(n):
-        tab = np.zeros((1, _rng.CROP_PARAM_FLOATS), np.float32)
-        tab[0, _rng.F_CSIZE] = h
-        tab[0, _rng.F_ROT:_rng.F_ROT + 4] = (1., 0., 0., 1.)
-        if transform.kind == _rng.TF_FAST:
-            tab[0, _rng.F_FLAGS] = _rng.draw_fast(tab[0], h)
-        tdev = torch.from_numpy(tab).to(x.device)
-        meta = (h, w, 0, 0, 1, h, transform.kind, 1.)
-        outs.append(_SliceImgs.apply(x[i:i + 1], tdev, meta))
-    return torch.cat(outs, 0)
+    tab = np.zeros((1, _rng.CROP_PARAM_FLOATS), np.float32)
+    tab[0, _rng.F_CSIZE] = h
+    tab[0, _rng.F_ROT:_rng.F_ROT + 4] = (1., 0., 0., 1.)
+    if transform.kind == _rng.TF_FAST:
+        tab[0, _rng.F_FLAGS] = _rng.draw_fast(tab[0], h)
+    tdev = torch.from_numpy(tab).to(x.device)
+    meta = (h, w, 0, 0, 1, h, transform.kind, 1.)
+    return torch.cat([_SliceImgs.apply(x[i:i + 1], tdev, meta) for i in range(n)], 0)
 
 
 # ---------------------------------------------------------------------------------------------- loss
@@ -159,10 +158,15 @@ def sim_func(v1, v2, type=None):
     elif type is None or not any(k in type for k in ('spher', 'ang', 'dot')):
         fused_kind = 0
     if fused_kind is not None and v1.is_cuda and v2.is_cuda and v1.dim() == 2 and v2.dim() == 2 and v1.shape[-1] == v2.shape[-1]:
+        out = None
         if v1.shape[0] in (1, v2.shape[0]):
-            return _SimFused.apply(v1, v2, fused_kind)
-        if v2.shape[0] == 1:                                 # both similarities are symmetric in their arguments
-            return _SimFused.apply(v2, v1, fused_kind)
+            out = _SimFused.apply(v1, v2, fused_kind)
+        elif v2.shape[0] == 1:                               # both similarities are symmetric in their arguments
+            out = _SimFused.apply(v2, v1, fused_kind)
+        if out is not None:
+            if _trace.enabled():
+                _trace.sim(out.item())
+            return out
     if type is not None and 'mix' in type:
         coss = torch.cosine_similarity(v1, v2, dim=-1).mean()
         a = F.normalize(v1, dim=-1); b = F.normalize(v2, dim=-1)
@@ -207,7 +211,12 @@ def _drain_saves():
 def _encode_save(fname, chw):
     from imageio import imsave
     img = np.transpose(chw, (1, 2, 0))
-    imsave(fname, np.clip(img * 255, 0, 255).astype(np.uint8))        # utils.py:98-100
+    # encode under a temporary name in the same directory, then rename: a reader of the directory (ffmpeg, img_list) never
+    # sees a half-written frame. The temporary keeps the extension so the encoder still picks the format from it.
+    base, ext = os.path.splitext(fname)
+    tmp = '%s.tmp%d%s' % (base, os.getpid(), ext)
+    imsave(tmp, np.clip(img * 255, 0, 255).astype(np.uint8))          # utils.py:98-100
+    os.replace(tmp, fname)
 
 
 def _submit_save(fname, chw):
@@ -251,17 +260,94 @@ def checkout(img, fname=None, verbose=False):
         _submit_save(fname, np.array(img, dtype=np.float32))           # private copy; conversion + encode happen off-thread
 
 
+class _Derivat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img):
+        x = img.detach().contiguous().float()
+        C, H, W = x.shape[0] * x.shape[1], x.shape[2], x.shape[3]
+        sums = torch.empty(2, device=x.device, dtype=torch.float64)
+        val = torch.empty((), device=x.device, dtype=torch.float32)
+        check(lib().aph_derivat_fwd(x.data_ptr(), C, H, W, sums.data_ptr(), val.data_ptr(), stream_ptr()), 'aph_derivat_fwd')
+        ctx.save_for_backward(x)
+        return val
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        up = g.detach().float().reshape(1).contiguous()
+        grad = torch.empty_like(x)
+        check(lib().aph_derivat_bwd(x.data_ptr(), x.shape[0] * x.shape[1], x.shape[2], x.shape[3], up.data_ptr(), grad.data_ptr(), stream_ptr()),
+              'aph_derivat_bwd')
+        return grad
+
+
 def derivat(img, mode='sobel'):
-    """utils.py:256-268 (the script only ever passes mode='naiv', i.e. the finite-difference branch)."""
+    """utils.py:256-268. clip_fft.py:272 only ever passes mode='naiv' (the finite-difference branch): one fused reduction
+    kernel + its adjoint (csrc/loss.cu). The kornia / conv2d modes are not provided."""
     if mode in ('scharr', 'sobel'):
         raise NotImplementedError('aphantasia_b200.derivat: only the finite-difference mode used by clip_fft.py is provided')
-    dx = torch.mean(torch.abs(img[:, :, :, 1:] - img[:, :, :, :-1]))
-    dy = torch.mean(torch.abs(img[:, :, 1:, :] - img[:, :, :-1, :]))
-    return 0.5 * (dx + dy)
+    require_cuda(img, 'derivat input')
+    assert img.dim() == 4 and img.shape[2] > 1 and img.shape[3] > 1, 'derivat expects [N,C,H,W]'
+    return _Derivat.apply(img)
 
 
-def aesthetic_model(clip_model='vit_b_32'):
-    raise NotImplementedError('aphantasia_b200: --aest downloads a checkpoint (no network here); out of the hot path')
+class _Head(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, w, b):
+        e = emb.detach().contiguous().float()
+        S, D = e.shape
+        out = torch.empty(S, 1, device=e.device, dtype=torch.float32)
+        check(lib().aph_head_fwd(e.data_ptr(), S, D, w.data_ptr(), b.data_ptr(), out.data_ptr(), stream_ptr()), 'aph_head_fwd')
+        ctx.save_for_backward(w)
+        ctx.shape = (S, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        w, = ctx.saved_tensors
+        S, D = ctx.shape
+        g = g.contiguous().float()
+        ge = torch.empty(S, D, device=g.device, dtype=torch.float32)
+        check(lib().aph_head_bwd(g.data_ptr(), w.data_ptr(), S, D, ge.data_ptr(), stream_ptr()), 'aph_head_bwd')
+        return ge, None, None
+
+
+class AestheticHead:
+    """What clip_fft.py needs from the nn.Linear(512, 1) the reference returns (utils.py:410-413): .cuda(), __call__([S,512]) -> [S,1]."""
+
+    def __init__(self, weight, bias, synthetic):
+        self.weight, self.bias, self.synthetic = weight.reshape(-1).float().contiguous(), bias.reshape(-1).float().contiguous(), synthetic
+
+    def cuda(self):
+        self.weight, self.bias = self.weight.cuda(), self.bias.cuda()
+        return self
+
+    def eval(self): return self
+    def half(self): return self
+    def float(self): return self
+
+    def __call__(self, emb):
+        require_cuda(emb, 'aesthetic head input')
+        if not self.weight.is_cuda:
+            self.cuda()
+        return _Head.apply(emb, self.weight, self.bias)
+
+
+def aesthetic_model(clip_model='ViT-B/32'):
+    """utils.py:402-413: the LAION linear aesthetic predictor on CLIP embeddings. The reference downloads
+    sa_0_4_<model>_linear.pth; here it is read from the working directory (the reference's own cache location) or
+    $APH_AEST_WEIGHTS if present, otherwise -- no network in this environment -- a seeded synthetic head is used, loudly."""
+    nf = 768 if clip_model == 'ViT-L/14' else 512 if clip_model in ['ViT-B/16', 'ViT-B/32'] else None
+    if nf is None:
+        return None
+    name = clip_model.replace('/', '_').replace('-', '_').lower()
+    for path in (os.environ.get('APH_AEST_WEIGHTS'), 'sa_0_4_%s_linear.pth' % name):
+        if path and os.path.isfile(path):
+            sd = torch.load(path, map_location='cpu')
+            return AestheticHead(sd['weight'], sd['bias'], False)
+    print(' [aphantasia_b200] no aesthetic-predictor weights (sa_0_4_%s_linear.pth) available: using a seeded synthetic linear head' % name)
+    g = torch.Generator().manual_seed(4321)
+    return AestheticHead((torch.rand(nf, generator=g) * 2 - 1) * nf ** -0.5, torch.zeros(1), True)
 
 
 def plot_text(txt, size=224):

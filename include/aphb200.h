@@ -175,10 +175,29 @@ int aph_prof_gemm(int enable, double* total_ms, double* total_flops, int* launch
 int aph_sim_fwd(const float* v1, int n1, const float* v2, int S, int D, int kind,
                 float* value, float* grad_v1, float* grad_v2, void* stream);
 
+/* ---- optional loss heads ---------------------------------------------------
+ * derivat(img, mode='naiv') (aphantasia/utils.py:256-268; clip_fft.py:271-272 --sharp): img [C,H,W];
+ * value = 0.5*(mean|d/dx| + mean|d/dy|); sums = double[2] device scratch. The backward multiplies by the
+ * upstream gradient read from a DEVICE scalar.                                                      */
+int aph_derivat_fwd(const float* img, int C, int H, int W, double* sums, float* value, void* stream);
+int aph_derivat_bwd(const float* img, int C, int H, int W, const float* upstream, float* grad_img, void* stream);
+/* Linear head on the embeddings: the LAION aesthetic predictor of --aest is nn.Linear(D, 1)
+ * (aphantasia/utils.py:402-413; clip_fft.py:255-256). out[s] = <emb_s, w> + b[0] (b may be NULL).   */
+int aph_head_fwd(const float* emb, int S, int D, const float* w, const float* b, float* out, void* stream);
+int aph_head_bwd(const float* grad_out, const float* w, int S, int D, float* grad_emb, void* stream);
+
 /* ================= step glue ==================================================================
  * torch.optim.Adam(betas=(b1,b2)) single-tensor update (clip_fft.py:108-115,295), bias-corrected. */
 int aph_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
                   float lr, float b1, float b2, float eps, int step, void* stream);
+
+/* aph_synth_fft_bwd with the Adam update of the spectrum fused into its last pass (the data
+ * gradient dP is in registers there): params / m / v [3,H,Wh,2] are updated in place; grad_params may be NULL
+ * (nothing is written) or receives dP as aph_synth_fft_bwd does. Same arithmetic as aph_adam_step.              */
+int aph_synth_fft_bwd_adam(aph_fft_plan* plan, const float* grad_out, const float* out, const float* x_raw,
+                           double* stats, const float* scale, float contrast, const float* colmat_host,
+                           int apply_sigmoid, float* grad_params, float* params, float* m, float* v,
+                           float lr, float b1, float b2, float eps, int step, void* stream);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches)                 */
 int64_t aph_launch_count(void);

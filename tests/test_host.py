@@ -159,3 +159,68 @@ def test_native_replay_in_place_numpy_state_equals_copy_path():
         _rng._NP_INPLACE = None
     assert _rng._numpy_state_address() is not None          # this NumPy exposes the expected mt19937_state layout
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+# ---------------------------------------------------------------------------------------------- launcher
+_LAUNCH_PROBE = '''
+import sys
+from aphantasia.image import to_valid_rgb, fft_image, dwt_image
+from aphantasia.utils import slice_imgs, sim_func
+from aphantasia import transforms
+import clip, aphantasia
+print("ORIGIN", aphantasia.__file__, sim_func.__module__, clip.load.__module__, sys.argv[1:])
+'''
+
+
+def _run_launcher(script, args, cwd):
+    import subprocess
+    env = dict(os.environ, APH_RUN_VERBOSE='1', PYTHONPATH=ROOT)
+    return subprocess.run([sys.executable, '-m', 'aphantasia_b200.run', script] + args, capture_output=True, text=True, timeout=300, cwd=cwd, env=env)
+
+
+def test_launcher_shadows_a_package_sitting_next_to_the_script(tmp_path):
+    """`python script.py` puts the script's directory first on sys.path, so an `aphantasia/` package beside the script (the
+    reference tree) would win over PYTHONPATH. The launcher must resolve the module names to dropin/ anyway."""
+    (tmp_path / 'aphantasia').mkdir()
+    (tmp_path / 'aphantasia' / '__init__.py').write_text('raise ImportError("the package next to the script was imported")\n')
+    (tmp_path / 'clip.py').write_text('raise ImportError("the clip module next to the script was imported")\n')
+    script = tmp_path / 'probe.py'
+    script.write_text(_LAUNCH_PROBE)
+    out = _run_launcher(str(script), ['--size', '224-224'], cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith('ORIGIN')][0]
+    assert os.path.join(ROOT, 'dropin', 'aphantasia') in line and 'aphantasia_b200.utils' in line and 'aphantasia_b200.clip' in line
+    assert "['--size', '224-224']" in line
+    assert 'aphantasia -> %s' % os.path.join(ROOT, 'dropin', 'aphantasia') in out.stderr
+
+
+@pytest.mark.skipif(not os.path.isfile('/root/reference/clip_fft.py'), reason='the reference tree only exists in the build container')
+def test_launcher_runs_the_real_clip_fft_imports():
+    """The unmodified /root/reference/clip_fft.py, started from INSIDE the reference tree: all of its top-level imports
+    (clip_fft.py:1-31) must resolve through the drop-in (argparse --help exits before any GPU work)."""
+    out = _run_launcher('/root/reference/clip_fft.py', ['--help'], cwd='/root/reference')
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert '--samples' in out.stdout and '--dualmod' in out.stdout
+    assert 'aphantasia -> %s' % os.path.join(ROOT, 'dropin', 'aphantasia') in out.stderr
+    assert 'clip -> %s' % os.path.join(ROOT, 'dropin', 'clip') in out.stderr
+
+
+@pytest.mark.parametrize('wave,N', [('coif1', 1), ('coif2', 2)])
+def test_tabulated_coiflets_have_their_defining_properties(wave, N):
+    """coifN (length 6N): orthonormal even shifts, sum sqrt(2), 2N vanishing wavelet moments, scaling-function moments
+    1..2N-1 vanishing about an integer centre. These conditions pin the filter up to reflection."""
+    from aphantasia_b200._wavelets import reconstruction_filters
+    rec_lo, rec_hi = reconstruction_filters(wave)
+    h = np.array(rec_lo[::-1], np.float64); L = len(h)
+    assert L == 6 * N and abs(h.sum() - np.sqrt(2)) < 1e-10
+    for m in range(L // 2):
+        assert abs(sum(h[k] * h[k + 2 * m] for k in range(L - 2 * m)) - (1. if m == 0 else 0.)) < 1e-10
+    g = np.array(rec_hi, np.float64)
+    for p in range(2 * N):
+        assert abs(sum(g[k] * float(k) ** p for k in range(L))) < 1e-8, 'wavelet moment %d' % p
+    hn = h / np.sqrt(2); c = sum(k * hn[k] for k in range(L))
+    assert abs(c - round(c)) < 1e-9
+    for p in range(1, 2 * N):
+        assert abs(sum(hn[k] * (k - c) ** p for k in range(L))) < 1e-8, 'scaling moment %d' % p
+    # PyWavelets relation between the reconstruction pair
+    assert np.allclose(g, [(-1) ** k * h[k] for k in range(L)])
