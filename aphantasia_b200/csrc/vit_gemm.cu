@@ -1,5 +1,6 @@
 // vit_gemm.cu -- host side of the tcgen05 GEMM (tensor-map encoding, launch) + the exported test entry.
 #include "tc_gemm.cuh"
+#include <atomic>
 #include <mutex>
 #include <vector>
 #include <utility>
@@ -73,10 +74,15 @@ static int sk_prepare() {
   return 0;
 }
 
+// launches per (tile variant, epilogue kind): variant 0 = 128x128 single CTA, 1 = 128x256 single CTA, 2 = 256x256 CTA pair.
+// Read by the tests to prove which kernel a shape really ran (aph_gemm_variant_launches).
+static std::atomic<long long> g_variant_launches[3][EPI_KINDS];
+
 template <int BN, int STAGES, int EPI, int CG = 1>
 static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi_in, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES, CG>;
   GemmEpi epi = epi_in;
+  g_variant_launches[CG == 2 ? 2 : (BN == 256 ? 1 : 0)][EPI].fetch_add(1, std::memory_order_relaxed);
   static bool configured = false;
   if (!configured) {
     APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -160,6 +166,27 @@ extern "C" int aph_gemm_bf16_tn(const void* A, const void* B, float* C, int M, i
   epi.out_f32 = C;
   { const char* e = getenv("APH_GEMM_NOSTORE"); epi.nostore = (e && e[0] == '1') ? 1 : 0; }
   return launch_gemm(A, B, GemmShape{M, N, K}, epi, (cudaStream_t)stream);
+}
+
+// Test entry: the encoder's GEMM with any of its fused epilogues, on caller-supplied operands (tests/test_gpu_bench_config.py).
+// Unused pointers are NULL; the combination selects the epilogue kind exactly as the encoder's own calls do.
+extern "C" int aph_gemm_epi_test(const void* A, const void* B, int M, int N, int K, const float* bias, const float* resid,
+                                 const void* gelu_in, int act, float* out_f32, void* out_bf16, void* out_pre,
+                                 int unpatch_p, int unpatch_g, void* stream) {
+  GemmEpi epi;
+  epi.bias = bias; epi.resid = resid; epi.gelu_in = reinterpret_cast<const bf16*>(gelu_in); epi.act = act;
+  epi.out_f32 = out_f32; epi.out_bf16 = reinterpret_cast<bf16*>(out_bf16); epi.out_pre = reinterpret_cast<bf16*>(out_pre);
+  epi.unpatch_p = unpatch_p; epi.unpatch_g = unpatch_g;
+  return launch_gemm(A, B, GemmShape{M, N, K}, epi, (cudaStream_t)stream);
+}
+
+// launches so far of tile variant `variant` (0: 128x128 single CTA, 1: 128x256 single CTA, 2: 256x256 cta_group::2 pair) with
+// epilogue kind `epi` (EPI_* order of tc_gemm.cuh: 0 f32, 1 bf16, 2 bias-bf16, 3 bias-gelu, 4 bias-resid, 5 gelugrad, 6 unpatch; -1 = all)
+extern "C" int64_t aph_gemm_variant_launches(int variant, int epi) {
+  if (variant < 0 || variant > 2 || epi >= EPI_KINDS) return -1;
+  long long n = 0;
+  for (int k = 0; k < EPI_KINDS; ++k) if (epi < 0 || epi == k) n += g_variant_launches[variant][k].load();
+  return (int64_t)n;
 }
 
 // Profiling aid for bench.py: enable=1 starts recording a CUDA-event pair around every GEMM launch (on its stream);

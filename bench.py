@@ -36,6 +36,8 @@ sys.path.insert(0, ROOT)
 H, W, SAMPLES_FLAG, MODEL, PATCH = 720, 1280, 200, 'ViT-B/32', 32
 S_TOTAL = int(SAMPLES_FLAG * 0.95)
 F_VIT = {32: 8.8176e9, 16: 35.1269e9}      # forward FLOPs per image
+# one workload string for BOTH arms (the driver compares config.workload of the two lines)
+WORKLOAD = 'clip_fft.py --size 1280-720 --samples 200 ViT-B/32 FFT: S=190 crops/step, transforms_fast, mix loss, Adam'
 
 
 def vit_gemm_shapes(S, patch=32, D=768, layers=12, out=512, res=224):
@@ -220,9 +222,9 @@ def usable_cpus():
     return max(1, min(n, 64))      # beyond 64 threads the per-crop ops of the reference only lose to thread overhead
 
 
-def cpu_baseline_port(sample_S, threads=None):
-    """Times the oracle port of the reference step on the host cores on a bounded sample (sample_S of the 190 crops,
-    full 1280x720 canvas) and extrapolates linearly in the crop count; synth fwd/bwd is measured at full size."""
+def _cpu_setup(threads=None):
+    """Inputs of the CPU arm: same seeds / shapes as DeviceStep (so its step-0 loss is comparable). The crop table comes from the
+    PYTHON specification of the RNG replay (_rng.draw_crop_table_py): nothing of libaphb200.so is loaded on this path."""
     from aphantasia_b200 import _rng
     from aphantasia_b200.clip import synthetic_visual_state_dict
     from oracle import restate as R
@@ -234,20 +236,47 @@ def cpu_baseline_port(sample_S, threads=None):
     vis = R.build_visual(synthetic_visual_state_dict(patch=PATCH, seed=0))
     g = torch.Generator().manual_seed(1234)
     txt = torch.randn(1, 512, generator=g); txt = 10. * txt / txt.norm()
-    tabs, _ = _rng.draw_crop_table(S_TOTAL, (H, W), 224, _rng.TF_FAST, 'uniform', 0.4)
+    tabs, _ = _rng.draw_crop_table_py(S_TOTAL, (H, W), 224, _rng.TF_FAST, 'uniform', 0.4)
 
     def step(S):
         t0 = time.perf_counter()
-        R.reference_step(params, scale, (H, W), cm, tabs[0][:S], vis, txt, 'mix')
-        return time.perf_counter() - t0
+        loss, _g, _e = R.reference_step(params, scale, (H, W), cm, tabs[0][:S], vis, txt, 'mix')
+        return time.perf_counter() - t0, float(loss)
+    return step, cores
+
+
+_SAMPLE_TXT = 'oracle/restate.py reference_step (torch fp32 on the host, incl. the CLIP weight-gradients the reference also computes), 1280x720 canvas, '
+
+
+def cpu_baseline_port(budget_s=30., threads=None, state=None):
+    """Times the oracle port of the reference step on the host cores. A FULL 190-crop step is timed when it fits `budget_s`
+    (then nothing is extrapolated); otherwise a crop sample is timed and scaled linearly in the crop count, and says so."""
+    step, cores = state or _cpu_setup(threads)
     step(1)                                          # warm-up (allocator, thread pool)
-    t1 = step(1)
-    tS = step(sample_S)
-    per_crop = max(tS - t1, 1e-9) / max(sample_S - 1, 1)
-    t_full = t1 + per_crop * (S_TOTAL - 1)
-    return {'value': 1.0 / t_full, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
-            'sample': 'oracle/restate.py reference_step (fp32, incl. the CLIP weight-gradients the reference also computes), 1280x720 canvas, '
-                      '%d of %d crops timed (%.2fs) + 1-crop step (%.2fs), extrapolated linearly in crops to %.2fs/step' % (sample_S, S_TOTAL, tS, t1, t_full)}
+    t1, _ = step(1)
+    t8, _ = step(8)
+    per_crop = max(t8 - t1, 1e-9) / 7.
+    est_full = t1 + per_crop * (S_TOTAL - 1)
+    if est_full <= budget_s:
+        t_full, loss = step(S_TOTAL)
+        return {'value': 1.0 / t_full, 'unit': 'steps/s', 'cores': cores, 'kind': 'port', 'extrapolated': False, 'crops_timed': S_TOTAL,
+                'step0_loss': loss, 'sample': _SAMPLE_TXT + 'one full %d-crop step timed: %.2fs' % (S_TOTAL, t_full)}
+    n = int(max(8, min(S_TOTAL, (budget_s - t1) / per_crop)))
+    tn, _ = step(n)
+    t_full = t1 + max(tn - t1, 1e-9) / max(n - 1, 1) * (S_TOTAL - 1)
+    return {'value': 1.0 / t_full, 'unit': 'steps/s', 'cores': cores, 'kind': 'port', 'extrapolated': True, 'crops_timed': n, 'step0_loss': None,
+            'sample': _SAMPLE_TXT + '%d of %d crops timed (%.2fs) + 1-crop step (%.2fs), extrapolated linearly in crops to %.2fs/step' % (n, S_TOTAL, tn, t1, t_full)}
+
+
+def gpu_eager_baseline(steps=3):
+    """Second baseline: the reference's op sequence as plain PyTorch-eager CUDA ops on THIS GPU (fp16 CLIP as
+    clip.load() gives on a GPU, incl. the weight gradients the reference computes) -- tests/eager_gpu_baseline.py."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('eager_gpu_baseline', os.path.join(ROOT, 'tests', 'eager_gpu_baseline.py'))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    r = mod.measure(steps, ('fp16_clip_with_weight_grads',))['fp16_clip_with_weight_grads']
+    return {'value': r['steps_per_s'], 'unit': 'steps/s', 'ms_per_step': r['ms_per_step'], 'steps': steps,
+            'what': 'same step as PyTorch-eager CUDA ops on the same GPU (per-crop interpolate / grid_sample loop, nn.MultiheadAttention CLIP in fp16 with weight gradients)'}
 
 
 def run_supplementary(args):
@@ -278,6 +307,12 @@ def run_ours(args):
 
     # ---- device-resident leg (value)
     ds = DeviceStep(hi - lo, S_TOTAL, rank, world, n_tables=min(K + Wm, 32))
+    loss0_dev = None
+    if world == 1:          # step-0 loss (= -sim) on the initial spectrum, before anything is updated: compared with the oracle's below
+        p0 = ds.params.clone()
+        ds.step(0); torch.cuda.synchronize()
+        loss0_dev = -float(ds.loss.item())
+        ds.params.copy_(p0); ds.m.zero_(); ds.v.zero_(); ds.t = 0
     clocks = ClockSampler(local) if rank == 0 else None
     l0 = _lib.lib().aph_launch_count()
     t_dev = timed(ds.step, K, Wm, barrier)
@@ -346,7 +381,7 @@ def run_ours(args):
         'metric': 'optimization steps/sec @1280x720 FFT, 200 samples, ViT-B/32', 'value': K / t_dev, 'unit': 'steps/s',
         'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': 1e3 * t_dev / K, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic (seeded spectrum, seeded synthetic ViT-B/32 weights, seeded text embedding)',
-        'config': {'workload': 'clip_fft.py --size 1280-720 --samples 200 ViT-B/32 FFT: S=190 crops/step, transforms_fast, mix loss, Adam',
+        'config': {'workload': WORKLOAD,
                    'parallelism': 'samples sharded over %d GPU(s), one NCCL all-reduce of dRGB per step' % world if world > 1 else 'single GPU',
                    'l2': 'working set per step (~1.9 GB of saved activations) exceeds the 126 MB L2; no explicit flush'},
         'e2e': {'value': K / t_api, 'unit': 'steps/s', 'h2d_bytes_per_step': (hi - lo) * 24 * 4, 'd2h_bytes_per_step': 4,
@@ -362,11 +397,20 @@ def run_ours(args):
                      'vit_step_frac': (flops_vit / (1e-3 * (stages.get('vit_fwd', 0) + stages.get('vit_bwd', 0)) + 1e-12)) / 1e12 / peak_tf},
         'stages_ms': {k: round(v, 4) for k, v in stages.items()},
     }
+    out['parity'] = {'step0_loss': loss0_dev, 'what': 'loss of the first device-resident step (seed 0); the oracle value of the same step is cpu_baseline.step0_loss'}
     if world == 1:
         try:
-            out['cpu_baseline'] = cpu_baseline_port(sample_S=8)
+            out['cpu_baseline'] = cpu_baseline_port()
+            ol = out['cpu_baseline'].get('step0_loss')
+            if ol is not None and loss0_dev is not None:
+                out['parity'].update({'oracle_step0_loss': ol, 'abs_diff': abs(ol - loss0_dev), 'tolerance': 2e-3})
         except Exception as ex:      # the baseline must never take the bench line down
             out['cpu_baseline'] = {'value': None, 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': 'failed: %r' % (ex,)}
+        if os.environ.get('APH_BENCH_EAGER', '1') == '1':
+            try:
+                out['gpu_eager_baseline'] = gpu_eager_baseline()
+            except Exception as ex:
+                out['gpu_eager_baseline'] = {'value': None, 'unit': 'steps/s', 'what': 'failed: %r' % (ex,)}
     print(json.dumps(out))
 
 
@@ -403,24 +447,36 @@ def run_reference(args):
     if rank != 0:
         return
     K, Wm = max(args.steps, 1), args.warmup
-    # bounded sample per step so that the whole run ends within a few minutes
-    budget = 150.0
-    probe = cpu_baseline_port(sample_S=2)
-    t_full = 1.0 / probe['value']
-    per_crop = t_full / S_TOTAL
-    sample_S = int(max(2, min(S_TOTAL, budget / max(K + Wm, 1) / max(per_crop, 1e-6))))
-    vals = []
+    state = _cpu_setup()
+    step, cores = state
+    step(1)
+    t1, _ = step(1)
+    t8, _ = step(8)
+    per_crop = max(t8 - t1, 1e-9) / 7.
+    est_full = t1 + per_crop * (S_TOTAL - 1)
+    budget = 240.0                                   # the whole --steps K --warmup W run must end within a few minutes
+    n = S_TOTAL if est_full * (K + Wm) <= budget else int(max(8, min(S_TOTAL, (budget / (K + Wm) - t1) / per_crop)))
+    times, loss0 = [], None
     for i in range(Wm + K):
-        r = cpu_baseline_port(sample_S=sample_S)
+        t, loss = step(n)
+        if i == 0:
+            loss0 = loss
         if i >= Wm:
-            vals.append(r['value'])
-    v = float(np.median(vals))
-    r['value'] = v
+            times.append(t)
+    t_n = float(np.median(times))
+    extrap = n < S_TOTAL
+    t_full = t_n if not extrap else t1 + max(t_n - t1, 1e-9) / max(n - 1, 1) * (S_TOTAL - 1)
+    v = 1.0 / t_full
+    cb = {'value': v, 'unit': 'steps/s', 'cores': cores, 'kind': 'port', 'extrapolated': extrap, 'crops_timed': n, 'steps_timed': K,
+          'step0_loss': loss0 if not extrap else None,
+          'sample': _SAMPLE_TXT + ('%d full %d-crop steps timed, median %.2fs' % (K, S_TOTAL, t_n) if not extrap else
+                                   '%d steps of %d of %d crops timed (median %.2fs), extrapolated linearly in crops to %.2fs/step' % (K, n, S_TOTAL, t_n, t_full))}
     out = {'impl': 'reference', 'metric': 'optimization steps/sec @1280x720 FFT, 200 samples, ViT-B/32', 'value': v, 'unit': 'steps/s',
            'n_gpus': args.gpus, 'steps': K, 'warmup': Wm, 'ms_per_step': 1e3 / v, 'higher_is_better': True, 'scaling': 'strong',
            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (same seeds / shapes as the GPU arm)',
-           'config': {'workload': 'clip_fft.py --size 1280-720 --samples 200 ViT-B/32 FFT: S=190 crops/step (CPU oracle port of the reference path)'},
-           'cpu_baseline': r, 'e2e': {'value': v, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+           'config': {'workload': WORKLOAD, 'arm': 'CPU oracle port of the reference path on %d host threads' % cores},
+           'extrapolated': extrap,
+           'cpu_baseline': cb, 'e2e': {'value': v, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(out))
 
 

@@ -163,6 +163,17 @@ int64_t aph_vit_bytes(const aph_vit* vit);
  * C[M,N] (fp32) = A[M,K] (bf16, row-major) . B[N,K]^T (bf16, row-major). K % 64 == 0, N % 128 == 0. */
 int aph_gemm_bf16_tn(const void* A, const void* B, float* C, int M, int N, int K, void* stream);
 
+/* Test entries. aph_gemm_epi_test: the same GEMM with the encoder's fused epilogues on caller-supplied operands
+ * (NULL = unused; the combination selects the kind as the encoder's own calls do: +bias, QuickGELU saving the
+ * pre-activation (act=1, out_pre), x gelu'(gelu_in), +fp32 resid, fp32 / bf16 outputs, NCHW un-patchify).
+ * aph_gemm_variant_launches: launches so far of tile variant 0 (128x128, one CTA), 1 (128x256, one CTA) or
+ * 2 (256x256, cta_group::2 pair) with epilogue kind epi (0 f32, 1 bf16, 2 bias-bf16, 3 bias-gelu, 4 bias-resid,
+ * 5 gelu-grad, 6 un-patchify; -1 = any).                                                             */
+int aph_gemm_epi_test(const void* A, const void* B, int M, int N, int K, const float* bias, const float* resid,
+                      const void* gelu_in, int act, float* out_f32, void* out_bf16, void* out_pre,
+                      int unpatch_p, int unpatch_g, void* stream);
+int64_t aph_gemm_variant_launches(int variant, int epi);
+
 /* Profiling aid: enable=1 records a CUDA-event pair around every GEMM launch of this library; enable=0 stops and returns
  * the summed kernel time (ms), FLOPs (sum of 2MNK) and launch count since enabling (bench.py's roofline).            */
 int aph_prof_gemm(int enable, double* total_ms, double* total_flops, int* launches);

@@ -21,11 +21,14 @@ sys.path.insert(0, ROOT)
 H, W, S = 720, 1280, 190
 
 
-def main():
+VARIANTS = (('fp16_clip_with_weight_grads', torch.float16, True), ('fp16_clip_frozen', torch.float16, False),
+            ('fp32_clip_frozen', torch.float32, False))
+
+
+def measure(steps=8, names=None):
     from aphantasia_b200 import _rng
     from aphantasia_b200.clip import synthetic_visual_state_dict
     from oracle import restate as R
-    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     torch.manual_seed(0); np.random.seed(0)
     tabs, _ = _rng.draw_crop_table(S, (H, W), 224, _rng.TF_FAST, 'uniform', 0.4)
     params0 = 0.01 * torch.randn(1, 3, H, W // 2 + 1, 2)
@@ -33,10 +36,12 @@ def main():
     g = torch.Generator().manual_seed(1234)
     txt = torch.randn(1, 512, generator=g); txt = (10. * txt / txt.norm()).cuda()
     sd = synthetic_visual_state_dict(patch=32, seed=0)
+    prev_dev = torch.get_default_device()
     torch.set_default_device('cuda')
     results = {}
-    for name, dtype, wgrad in (('fp16_clip_with_weight_grads', torch.float16, True), ('fp16_clip_frozen', torch.float16, False),
-                               ('fp32_clip_frozen', torch.float32, False)):
+    for name, dtype, wgrad in VARIANTS:
+        if names is not None and name not in names:
+            continue
         vis = R.build_visual(sd).cuda()
         if dtype == torch.float16:                   # clip.model.convert_weights: everything but the LayerNorms goes to fp16
             vis.half()
@@ -69,6 +74,13 @@ def main():
         results[name] = {'steps_per_s': 1.0 / t, 'ms_per_step': 1e3 * t, 'loss': last}
         del vis, p, opt
         torch.cuda.empty_cache()
+    torch.set_default_device(prev_dev)
+    return results
+
+
+def main():
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    results = measure(steps)
     print(json.dumps({'workload': 'C2: 1280x720 FFT, S=190, ViT-B/32, transforms_fast, mix loss, Adam; PyTorch-eager CUDA ops (oracle restatement)',
                       'steps': steps, 'device': torch.cuda.get_device_name(0), 'results': results}))
 

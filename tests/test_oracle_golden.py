@@ -142,3 +142,18 @@ def test_vit_restatement_matches_hf():
     assert _rel(a.detach(), b.detach()) < 1e-5
     ga, = torch.autograd.grad(a.sum(), x); gb, = torch.autograd.grad(b.sum(), x)
     assert _rel(ga, gb) < 1e-4
+
+
+@pytest.mark.parametrize('wave', ['db3', 'coif1', 'coif2'])
+def test_dwt_restatement_perfect_reconstruction_unpinned(wave):
+    """PARITY UNPINNED (pytorch_wavelets / PyWavelets absent): the restated symmetric-mode analysis bank followed by the restated
+    DWTInverse must give the identity; this checks self-consistency of filters and conventions, not the third party's band order."""
+    rec_lo, rec_hi = R.wavelet_filters(wave)
+    dec_lo, dec_hi = rec_lo[::-1], rec_hi[::-1]
+    torch.manual_seed(0)
+    x = torch.randn(1, 3, 40, 52, dtype=torch.float64)
+    lo, hi = R.afb1d_sym(x, dec_lo, dec_hi, 3)
+    ll, lh = R.afb1d_sym(lo, dec_lo, dec_hi, 2)
+    hl, hh = R.afb1d_sym(hi, dec_lo, dec_hi, 2)
+    y = R.dwt_inverse(ll, [torch.stack([lh, hl, hh], 2)], rec_lo, rec_hi)
+    assert y.shape == x.shape and _rel(y, x) < 1e-9
