@@ -49,6 +49,7 @@ struct VitImpl {
   bf16* h_act = nullptr;         // [M, 4D]
   float *st_mean = nullptr, *st_rstd = nullptr;   // [(2*layers+2)][M]
   bf16* cls_ln = nullptr;        // [S, D]
+  float* emb_int = nullptr;      // [S, out] (copied to the caller's buffer outside the graph)
   // backward scratch
   bf16* d_emb = nullptr;         // [S, out]
   float* d_cls = nullptr;        // [S, D]
@@ -220,7 +221,7 @@ extern "C" int aph_vit_create(aph_vit** out, const aph_vit_config* cfg) {
   v->qkv.resize(Ly); v->h_pre.resize(Ly);
   for (int i = 0; i < Ly; ++i) { e |= dev_alloc(v, &v->qkv[i], M * 3 * D); e |= dev_alloc(v, &v->h_pre[i], M * 4 * D); }
   e |= dev_alloc(v, &v->st_mean, (size_t)(2 * Ly + 2) * M); e |= dev_alloc(v, &v->st_rstd, (size_t)(2 * Ly + 2) * M);
-  e |= dev_alloc(v, &v->cls_ln, (size_t)S * D);
+  e |= dev_alloc(v, &v->cls_ln, (size_t)S * D); e |= dev_alloc(v, &v->emb_int, (size_t)S * O);
   e |= dev_alloc(v, &v->d_emb, (size_t)S * O); e |= dev_alloc(v, &v->d_cls, (size_t)S * D);
   e |= dev_alloc(v, &v->dx, M * D); e |= dev_alloc(v, &v->dx_bf, M * D); e |= dev_alloc(v, &v->dh, M * 4 * D);
   e |= dev_alloc(v, &v->d_ln, M * D); e |= dev_alloc(v, &v->d_attn, M * D); e |= dev_alloc(v, &v->d_qkv, M * 3 * D);
@@ -309,16 +310,22 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
   APH_REQUIRE(v->finalized, "aph_vit_fwd: weights not finalized");
   APH_REQUIRE(S > 0 && S <= v->cfg.max_batch, "aph_vit_fwd: S=%d outside (0, max_batch=%d]", S, v->cfg.max_batch);
   cudaStream_t st = (cudaStream_t)stream;
-  const int rc = run_cached(v->fwd_graphs, v->warm_fwd, v->stamp, v->graph_misses, images, emb, S, save_for_bwd, st, [&]() -> int {
+  // The only kernels that touch caller-owned memory (k_patchify reads `images`, the last copy writes `emb`) run OUTSIDE the cached
+  // graph, so the graph is keyed on the batch size alone: a caller whose tensors move every step (clip_fft.py:285 calls
+  // torch.cuda.empty_cache() per step) still replays it.
+  {
+    const int g = v->g, Mp = S * g * g;
+    const size_t n8 = (size_t)Mp * v->Kp / 8;
+    APH_CUDA_OK(launch_k(k_patchify, dim3((unsigned)std::min<size_t>((n8 + 255) / 256, (size_t)kNumSMs * 16)), dim3(256), (size_t)0, st, 1, images, v->patches, S, v->cfg.patch, g));
+    APH_LAUNCH_OK();
+  }
+  const int rc = run_cached(v->fwd_graphs, v->warm_fwd, v->stamp, v->graph_misses, nullptr, nullptr, S, save_for_bwd, st, [&]() -> int {
   const int D = v->D, T = v->T, g = v->g, Ly = v->cfg.layers, O = v->cfg.out_dim, H = v->cfg.heads;
   const int M = S * T, Mp = S * g * g;
   const size_t Mmax = (size_t)v->cfg.max_batch * T;
   int e;
   // patch embedding
   {
-    const size_t n8 = (size_t)Mp * v->Kp / 8;
-    APH_CUDA_OK(launch_k(k_patchify, dim3((unsigned)std::min<size_t>((n8 + 255) / 256, (size_t)kNumSMs * 16)), dim3(256), (size_t)0, st, 1, images, v->patches, S, v->cfg.patch, g));
-    APH_LAUNCH_OK();
     GemmEpi ep; ep.out_f32 = v->tok;
     if ((e = launch_gemm(v->patches, v->w_conv, GemmShape{Mp, D, v->Kp}, ep, st))) return e;
     NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_embed_lnpre<NCH>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, v->tok, v->cls, v->pos, v->lnpre_w, v->lnpre_b, v->e, v->xs[0],
@@ -350,12 +357,13 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
     NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_fwd<NCH>, dim3(rows_grid(S)), dim3(256), (size_t)0, st, 1, v->xs[2 * Ly], (size_t)T * D, v->lnpost_w, v->lnpost_b, v->cls_ln,
                                                                  meanp, rstdp, S, D)));
     APH_LAUNCH_OK();
-    GemmEpi ep; ep.out_f32 = emb;
+    GemmEpi ep; ep.out_f32 = v->emb_int;
     if ((e = launch_gemm(v->cls_ln, v->w_out, GemmShape{S, O, D}, ep, st))) return e;
   }
   return 0;
   });
   if (rc) return rc;
+  APH_CUDA_OK(cudaMemcpyAsync(emb, v->emb_int, (size_t)S * v->cfg.out_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
   v->last_S = save_for_bwd ? S : -1;
   return 0;
 }
@@ -365,15 +373,17 @@ extern "C" int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* gr
   VitImpl* v = reinterpret_cast<VitImpl*>(vit);
   APH_REQUIRE(v->last_S == S, "aph_vit_bwd: no saved forward for S=%d (last saved S=%d)", S, v->last_S);
   cudaStream_t st = (cudaStream_t)stream;
-  return run_cached(v->bwd_graphs, v->warm_bwd, v->stamp, v->graph_misses, grad_emb, grad_images, S, 0, st, [&]() -> int {
-  const int D = v->D, T = v->T, g = v->g, Ly = v->cfg.layers, O = v->cfg.out_dim, H = v->cfg.heads;
-  const int M = S * T, Mp = S * g * g;
+  {   // caller-owned input: converted outside the cached graph (see aph_vit_fwd)
+    const size_t n = (size_t)S * v->cfg.out_dim;
+    APH_CUDA_OK(launch_k(k_f32_to_bf16, dim3((int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8)), dim3(256), (size_t)0, st, 1, grad_emb, v->d_emb, n));
+    APH_LAUNCH_OK();
+  }
+  const int rc = run_cached(v->bwd_graphs, v->warm_bwd, v->stamp, v->graph_misses, nullptr, nullptr, S, 0, st, [&]() -> int {
+  const int D = v->D, T = v->T, Ly = v->cfg.layers, O = v->cfg.out_dim, H = v->cfg.heads;
+  const int M = S * T;
   const size_t Mmax = (size_t)v->cfg.max_batch * T;
   int e;
   {
-    const size_t n = (size_t)S * O;
-    APH_CUDA_OK(launch_k(k_f32_to_bf16, dim3((int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8)), dim3(256), (size_t)0, st, 1, grad_emb, v->d_emb, n));
-    APH_LAUNCH_OK();
     GemmEpi ep; ep.out_f32 = v->d_cls;
     if ((e = launch_gemm(v->d_emb, v->w_out_t, GemmShape{S, D, O}, ep, st))) return e;
     APH_CUDA_OK(cudaMemsetAsync(v->dx, 0, (size_t)M * D * sizeof(float), st));
@@ -408,8 +418,12 @@ extern "C" int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* gr
   // ln_pre backward (cls rows dropped) and patch-embed data gradient scattered back to NCHW
   NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_bwd<NCH>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, v->dx, v->e, v->st_mean, v->st_rstd, v->lnpre_w, nullptr, v->d_tok, M, T, D, 2, 0)));
   APH_LAUNCH_OK();
-  { GemmEpi ep; ep.out_f32 = grad_images; ep.unpatch_p = v->cfg.patch; ep.unpatch_g = g;
-    if ((e = launch_gemm(v->d_tok, v->w_conv_t, GemmShape{Mp, v->Kp, D}, ep, st))) return e; }
   return 0;
   });
+  if (rc) return rc;
+  // caller-owned output: the patch-embed data gradient (un-patchify epilogue writes NCHW) is launched outside the graph
+  { const int g = v->g, Mp = S * g * g;
+    GemmEpi ep; ep.out_f32 = grad_images; ep.unpatch_p = v->cfg.patch; ep.unpatch_g = g;
+    if (int e = launch_gemm(v->d_tok, v->w_conv_t, GemmShape{Mp, v->Kp, v->D}, ep, st)) return e; }
+  return 0;
 }

@@ -224,6 +224,15 @@ class _ValidRGB(torch.autograd.Function):
         return gi, None
 
 
+def _maybe_preview(t):
+    """Under torch.no_grad() (the script's preview branch, clip_fft.py:298-299) hand back a tensor whose .cpu() uses the pinned
+    read-back ring (utils.PreviewTensor, row f1)."""
+    if not torch.is_grad_enabled() and t.is_cuda and not t.requires_grad:
+        from .utils import PreviewTensor
+        return t.as_subclass(PreviewTensor)
+    return t
+
+
 def to_valid_rgb(image_f, colors=1., decorrelate=True):
     """Drop-in for image.py:14-29. Fuses colour decorrelation + sigmoid into the synthesis kernel when
     `image_f` is one of ours; otherwise applies the stand-alone kernel to whatever image_f returns."""
@@ -234,8 +243,8 @@ def to_valid_rgb(image_f, colors=1., decorrelate=True):
             shift = args[0] if len(args) > 0 else kwargs.get('shift', None)
             contrast = args[1] if len(args) > 1 else kwargs.get('contrast', 1.)
             if isinstance(image_f, PixelImage):
-                return image_f.fused(shift, contrast, colmat, True, args[2] if len(args) > 2 else kwargs.get('fixcontrast', False))
-            return image_f.fused(shift, contrast, colmat, True)
+                return _maybe_preview(image_f.fused(shift, contrast, colmat, True, args[2] if len(args) > 2 else kwargs.get('fixcontrast', False)))
+            return _maybe_preview(image_f.fused(shift, contrast, colmat, True))
         return _ValidRGB.apply(image_f(*args, **kwargs), colmat)
     return inner
 

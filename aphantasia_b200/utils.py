@@ -196,11 +196,72 @@ def basename(file):
     return os.path.splitext(os.path.basename(file))[0]
 
 
-# ---- preview write-out (clip_fft.py:297-306 runs it every `opt_step`, default every step): the JPEG encode of a
-# 1280x720 frame costs ~20-30 ms on the host -- several GPU steps. It is handed to a small thread pool so the optimisation
-# loop only pays for the array hand-over; readers of the output directory (img_list) and interpreter exit drain the queue.
+# ---- preview read-back and write-out. clip_fft.py:297-306 runs, every `opt_step` (default: EVERY step),
+#   img = image_f(contrast=a.contrast).cpu().numpy()[0];  checkout(img, '%04d.jpg')
+# i.e. a forward-only synthesis, an 11 MB device->host read-back and a JPEG encode (~25 ms on the host -- several GPU steps).
+# Here (i) image_f under no_grad returns a tensor whose .cpu() lands in a ring of PINNED host buffers (one async copy + one event
+# wait instead of a pageable staging copy), (ii) checkout() recognises a view of such a buffer and hands it to the encoder pool
+# WITHOUT copying it, (iii) clip / convert / JPEG-encode run on the pool. A ring slot is reused only when nothing references it
+# any more (the encoder's reference and the script's `img` both gone), so holding on to a frame stays safe.
 _pending = []
 _pool = None
+
+
+class _PinnedFrame(torch.Tensor):
+    """CPU tensor living in a pinned ring slot; .numpy() returns the slot's ONE ndarray object, so that views of it
+    (`.numpy()[0]`) keep that object referenced and the ring can tell when a slot is free again."""
+    _aph_arr = None
+
+    def numpy(self, *args, **kwargs):
+        return self._aph_arr
+
+
+class _PreviewRing:
+    MAX_SLOTS = 24
+
+    def __init__(self):
+        self.slots = {}                      # shape -> [(pinned CPU tensor, its ndarray), ...]
+
+    def owner_of(self, arr):
+        """True if `arr` (an ndarray) is a view of a ring slot."""
+        b = arr
+        while isinstance(b, np.ndarray) and b.base is not None and isinstance(b.base, np.ndarray):
+            b = b.base
+        return any(b is a for ring in self.slots.values() for (_t, a) in ring)
+
+    def fetch(self, dev_tensor):
+        import sys
+        shape = tuple(dev_tensor.shape)
+        ring = self.slots.setdefault(shape, [])
+        slot = None
+        for entry in ring:
+            if sys.getrefcount(entry[1]) <= 2:     # the ring's tuple + getrefcount's argument: no view of the slot is alive
+                slot = entry
+                break
+        plain = dev_tensor.as_subclass(torch.Tensor)
+        if slot is None:
+            if len(ring) >= self.MAX_SLOTS:        # every slot is still referenced (encoder backlog): ordinary pageable copy
+                return plain.cpu()
+            t = torch.empty(shape, dtype=dev_tensor.dtype).pin_memory()
+            slot = (t, t.numpy())
+            ring.append(slot)
+        slot[0].copy_(plain, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(); ev.synchronize()
+        out = slot[0].as_subclass(_PinnedFrame)
+        out._aph_arr = slot[1]
+        return out
+
+
+_ring = _PreviewRing()
+
+
+class PreviewTensor(torch.Tensor):
+    """What image_f returns under torch.no_grad(): an ordinary CUDA tensor whose .cpu() uses the pinned ring."""
+
+    def cpu(self, *args, **kwargs):
+        if args or kwargs or not self.is_cuda:
+            return self.as_subclass(torch.Tensor).cpu(*args, **kwargs)
+        return _ring.fetch(self)
 
 
 def _drain_saves():
@@ -227,8 +288,11 @@ def _submit_save(fname, chw):
     if _pool is None:
         import atexit
         from concurrent.futures import ThreadPoolExecutor
-        _pool = ThreadPoolExecutor(max_workers=int(os.environ.get('APH_SAVE_THREADS', '4')))
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 4)
+        _pool = ThreadPoolExecutor(max_workers=int(os.environ.get('APH_SAVE_THREADS', str(max(2, min(8, ncpu // 2))))))
         atexit.register(_drain_saves)
+    while _pending and _pending[0].done():
+        _pending.pop(0).result()
     while len(_pending) > 64:          # bound the queue (and host memory) if the encoder cannot keep up
         _pending.pop(0).result()
     _pending.append(_pool.submit(_encode_save, fname, chw))
@@ -257,7 +321,10 @@ def img_read(path):
 def checkout(img, fname=None, verbose=False):
     """utils.py:94-100: CHW float -> HWC uint8 -> file (rank 0 only under torchrun). The cv2 preview is dropped."""
     if fname is not None and _dist.rank() == 0:
-        _submit_save(fname, np.array(img, dtype=np.float32))           # private copy; conversion + encode happen off-thread
+        if isinstance(img, np.ndarray) and img.dtype == np.float32 and _ring.owner_of(img):
+            _submit_save(fname, img)                                   # a view of a pinned ring slot: no copy, the slot stays referenced
+        else:
+            _submit_save(fname, np.array(img, dtype=np.float32))       # private copy; conversion + encode happen off-thread
 
 
 class _Derivat(torch.autograd.Function):

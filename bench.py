@@ -196,6 +196,25 @@ class ApiStep:
         self.opt.step()
         return loss.item()                          # D2H read of the step's result
 
+    def script_step(self, i, opt_step, outdir):
+        """train(i) of the unmodified script, statement for statement (clip_fft.py:235-306): incl. the per-step
+        torch.cuda.empty_cache() (:285) and, every `opt_step`, the preview branch: second synthesis under no_grad, read-back,
+        checkout() -> JPEG (:297-306). No loss read-back: the script never reads its loss."""
+        from aphantasia_b200.utils import checkout
+        img_out = self.image_f(None)
+        img_sliced = self.slice_imgs([img_out], self.S, 224, self.tf, 'uniform', 0.4)[0]
+        out_enc = self.model.encode_image(img_sliced)
+        loss = 0
+        loss += -1. * 1. * self.sim_func(self.txt, out_enc, self.sim)
+        del img_out, img_sliced, out_enc; torch.cuda.empty_cache()
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        if i % opt_step == 0:
+            with torch.no_grad():
+                img = self.image_f(contrast=1.1).cpu().numpy()[0]
+            checkout(img, os.path.join(outdir, '%04d.jpg' % (i // opt_step)), verbose=False)
+
 
 def timed(fn, steps, warmup, dist_barrier):
     for i in range(warmup):
@@ -358,6 +377,27 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_api = float(t.item())
+    # the same loop exactly as the unmodified script runs it (empty_cache per step, preview every opt_step), wall-clock incl. the
+    # asynchronous JPEG encoder's drain: what a user of clip_fft.py sees at the default --opt_step 1 and at --opt_step 50
+    script = {}
+    if world == 1 and os.environ.get('APH_BENCH_SCRIPT', '1') == '1':
+        import shutil, tempfile
+        from aphantasia_b200.utils import _drain_saves
+        for ops in (1, 50):
+            d = tempfile.mkdtemp(prefix='aph_bench_')
+            try:
+                n = max(K, 50)
+                for i in range(5):
+                    api.script_step(i, ops, d)
+                _drain_saves(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for i in range(n):
+                    api.script_step(i, ops, d)
+                torch.cuda.synchronize(); _drain_saves()
+                dt = time.perf_counter() - t0
+                script['opt_step_%d' % ops] = {'value': n / dt, 'unit': 'steps/s', 'steps': n, 'frames_written': len(os.listdir(d))}
+            finally:
+                shutil.rmtree(d, ignore_errors=True)
 
     if world > 1:
         dist.barrier()
@@ -386,6 +426,7 @@ def run_ours(args):
                    'l2': 'working set per step (~1.9 GB of saved activations) exceeds the 126 MB L2; no explicit flush'},
         'e2e': {'value': K / t_api, 'unit': 'steps/s', 'h2d_bytes_per_step': (hi - lo) * 24 * 4, 'd2h_bytes_per_step': 4,
                 'ms_per_step': 1e3 * t_api / K, 'path': 'fft_image/to_valid_rgb/slice_imgs/encode_image/sim_func + backward + torch.optim.Adam'},
+        'e2e_script': script or None,
         'gpu_launches': int(launches),
         'clocks': clk,
         'roofline': {'bound': 'tensor', 'kernel': 'k_gemm_bf16_tn (tcgen05): all %d launches of one step, CUDA-event pair around each launch '
