@@ -15,7 +15,7 @@ from collections import OrderedDict
 
 import torch
 
-from .. import _trace
+from .. import _pool, _trace
 from .._lib import VitConfig, check, lib, require_cuda, stream_ptr
 
 _MODELS = {'ViT-B/32': dict(patch=32, width=768, layers=12, heads=12, out_dim=512, res=224),
@@ -66,7 +66,7 @@ class _EncodeImage(torch.autograd.Function):
         xi = x.detach().contiguous().float()
         S = xi.shape[0]
         vis._ensure(S)
-        emb = torch.empty(S, vis.output_dim, device=xi.device, dtype=torch.float32)
+        emb = _pool.empty((S, vis.output_dim))
         need_bwd = x.requires_grad
         check(lib().aph_vit_fwd(vis.handle, xi.data_ptr(), S, emb.data_ptr(), int(need_bwd), stream_ptr()), 'aph_vit_fwd')
         _trace.encode()
@@ -93,7 +93,7 @@ class _EncodeImage(torch.autograd.Function):
             check(lib().aph_vit_fwd(vis.handle, xi.data_ptr(), ctx.S, scratch.data_ptr(), 1, stream_ptr()), 'aph_vit_fwd (recompute)')
             vis._generation += 1            # the arena now belongs to this call; any other pending backward must recompute too
             vis.recomputes += 1
-        gi = torch.empty(ctx.shape, device=g.device, dtype=torch.float32)
+        gi = _pool.empty(ctx.shape)
         check(lib().aph_vit_bwd(vis.handle, g.data_ptr(), ctx.S, gi.data_ptr(), stream_ptr()), 'aph_vit_bwd')
         return gi, None
 

@@ -10,7 +10,14 @@
 //   warps 4-7        epilogue     : tcgen05.ld 32x32b -> registers -> fused epilogue -> global
 // Fused epilogues (struct GemmEpi): +bias, QuickGELU (saving the pre-activation), x gelu'(h) for the MLP
 // backward, +fp32 residual, fp32 and/or bf16 outputs, and an NCHW "un-patchify" store for the patch-embed
-// data gradient. Rows >= M are zero-filled by TMA on load and masked on store.
+// data gradient. Rows >= M are zero-filled by TMA on load and clipped by TMA on store.
+//
+// Epilogue data path (all kinds but the un-patchify scatter): each epilogue warp owns a ring of 4 KB shared-memory tiles
+// (32 rows x 128 B, the TMA 128B-swizzle layout). Outputs are packed in registers (bf16 kinds: 64 columns per tile),
+// written once to a ring tile and leave through cp.async.bulk.tensor stores (one elected lane, bulk groups, L2 cache
+// hints per tensor); the global operands of the fused kinds (fp32 residual, saved bf16 pre-activation) ARRIVE through
+// TMA loads into the same ring, issued one item ahead -- also across tile boundaries, i.e. during the next tile's main
+// loop -- and are combined IN PLACE, so no epilogue warp ever waits on a global load or issues a global store itself.
 #pragma once
 #include "aph_common.cuh"
 #include <cuda.h>
@@ -29,32 +36,6 @@ struct GemmEpi {
   int act = 0;                     // 1 = QuickGELU x*sigmoid(1.702x)
   int unpatch_p = 0;               // >0: out_f32 is [S,3,R,R]; row = s*g*g + gy*g + gx, col = c*p*p + py*p + px
   int unpatch_g = 0;
-  int nostore = 0;                 // profiling experiment: epilogue does everything but the global stores
-  // stream-K (set by launch_gemm): CTA groups own contiguous ranges of (tile, k-block) units; a tile split between two
-  // groups is finished by the group holding its first k-blocks, the other parks its fp32 partial in sk_ws
-  int sk = 0;
-  float* sk_ws = nullptr;          // [groups * CG][128][BN] fp32 partial accumulators
-  int* sk_flags = nullptr;         // [groups * CG][8] per-epilogue-warp ready flags (self-resetting)
-};
-
-// Work list of one CTA group: identical in the producer, MMA and epilogue roles.
-struct WorkIter {
-  int sk, G, num_tiles, kblocks, u, u1, tile_rr;
-  __device__ __forceinline__ void init(int sk_, int g, int G_, int num_tiles_, int kblocks_) {
-    sk = sk_; G = G_; num_tiles = num_tiles_; kblocks = kblocks_; tile_rr = g;
-    const long long U = (long long)num_tiles_ * kblocks_;
-    u = (int)((long long)g * U / G_); u1 = (int)((long long)(g + 1) * U / G_);
-  }
-  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
-    if (sk) {
-      if (u >= u1) return false;
-      tile = u / kblocks; kb0 = u - tile * kblocks; kb1 = min(kblocks, kb0 + (u1 - u)); u += kb1 - kb0;
-      return true;
-    }
-    if (tile_rr >= num_tiles) return false;
-    tile = tile_rr; kb0 = 0; kb1 = kblocks; tile_rr += G;
-    return true;
-  }
 };
 
 struct GemmShape { int M, N, K; };
@@ -241,21 +222,65 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return v;
 }
 
-template <int BN, int STAGES, int CG = 1>
+// ---- bulk-tensor stores (epilogue) ----------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_saddr, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_saddr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, uint32_t src_saddr, int x, int y, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_saddr), "r"(x), "r"(y), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// blocks until at most N of this thread's bulk groups still have to READ their shared-memory source
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// 2-D tile load into this CTA's shared memory, completion on a local mbarrier (epilogue operands)
+__device__ __forceinline__ void tma_load_2d_cta(uint32_t dst_saddr, const CUtensorMap* m, uint64_t* bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+constexpr int EPI_TILE_BYTES = 32 * 128;      // one ring tile: 32 rows x 128 B
+
+template <int BN, int STAGES, int CG, int NBUF>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;      // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;          // 4 epilogue warps x (32 rows x 128 B) transpose staging
-  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 32 * 128;
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;          // per epilogue warp: NBUF ring tiles
+  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * NBUF * EPI_TILE_BYTES;
   static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + GEMM_EPI_WARPS * NBUF;
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;   // + alignment slack
 };
 
-template <int BN, int STAGES, int EPI, int CG = 1>
+// compile-time properties of an epilogue kind
+template <int EPI> struct EpiTraits {
+  static constexpr bool OUT16 = (EPI == EPI_BF16 || EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_GELUGRAD_BF16);
+  static constexpr bool HAS_OP = (EPI == EPI_BIAS_RESID || EPI == EPI_GELUGRAD_BF16);      // a global operand arrives by TMA
+  static constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID);
+  static constexpr int NOUT = (EPI == EPI_BIAS_GELU) ? 2 : 1;
+  static constexpr int CW = OUT16 ? 64 : 32;                   // accumulator columns per ring tile
+  static constexpr int NBUF = (HAS_OP || NOUT == 2) ? 3 : 2;   // ring depth
+  static constexpr int STAGES = (NBUF == 3) ? 4 : 5;           // main-loop stages that still fit beside the ring (227 KB)
+};
+
+template <int BN, int STAGES, int EPI, int CG, int NBUF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape shp, GemmEpi epi) {
-  using L = GemmSmem<BN, STAGES, CG>;
+k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_o1, const __grid_constant__ CUtensorMap map_o2,
+               const __grid_constant__ CUtensorMap map_op, GemmShape shp, GemmEpi epi) {
+  using L = GemmSmem<BN, STAGES, CG, NBUF>;
+  using E = EpiTraits<EPI>;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -263,7 +288,8 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* op_bar = tempty_bar + 2;            // [GEMM_EPI_WARPS][NBUF] epilogue operand landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(op_bar + GEMM_EPI_WARPS * NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;      // position inside the CTA pair (0 = leader)
@@ -273,10 +299,16 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
+    if (EPI != EPI_UNPATCH) tma_prefetch_desc(&map_o1);
+    if (E::NOUT == 2) tma_prefetch_desc(&map_o2);
+    if (E::HAS_OP) tma_prefetch_desc(&map_op);
+  }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], CG); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CG * GEMM_EPI_WARPS); }
+    for (int i = 0; i < GEMM_EPI_WARPS * NBUF; ++i) mbar_init(&op_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) { if (CG == 2) tmem_alloc_cg2(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
@@ -291,11 +323,9 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ===== TMA producer
       const uint64_t pol_b = l2_policy_evict_last();      // B = weights: shared by all M tiles
       uint32_t it = 0;
-      WorkIter wi; wi.init(epi.sk, tile0, tile_step, num_tiles, k_blocks);
-      int tile, kb0, kb1;
-      while (wi.next(tile, kb0, kb1)) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = (tile / n_tiles) * CG + (int)rank, n_blk = tile % n_tiles;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
@@ -318,14 +348,12 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ===== MMA issuer (the leader CTA issues for the pair when CG = 2)
       constexpr uint32_t idesc = make_idesc_bf16(BN, GEMM_BM * CG);
       uint32_t it = 0, tile_iter = 0;
-      WorkIter wi; wi.init(epi.sk, tile0, tile_step, num_tiles, k_blocks);
-      int tile, kb0, kb1;
-      for (; wi.next(tile, kb0, kb1); ++tile_iter) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_iter) {
         const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph_ ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -334,195 +362,39 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < GEMM_BK / GEMM_UK; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (>>4) address field
-            if (CG == 2) umma_f16_cg2(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0);
-            else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0);
+            if (CG == 2) umma_f16_cg2(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
           if (CG == 2) {
-            umma_commit_mc(&empty_bar[s], 0b11);                          // both CTAs' smem stages are free
-            if (kb == kb1 - 1) umma_commit_mc(&tfull_bar[as], 0b11);   // both CTAs' epilogues may read TMEM
+            umma_commit_mc(&empty_bar[s], 0b11);                            // both CTAs' smem stages are free
+            if (kb == k_blocks - 1) umma_commit_mc(&tfull_bar[as], 0b11);   // both CTAs' epilogues may read TMEM
           } else {
-            umma_commit(&empty_bar[s]);                   // smem stage free once these MMAs retire
-            if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);   // accumulator (or this group's partial) complete
+            umma_commit(&empty_bar[s]);                                     // smem stage free once these MMAs retire
+            if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);            // accumulator complete
           }
         }
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: 8 warps. Warp w reads TMEM lanes 32*(w%4) .. +31 (one accumulator row per lane) and owns the 32-column
-    // chunks c = half, half+2, ... (half = (w-4)/4). Each 32x32 fp32 chunk is transposed through a swizzled shared-memory tile
-    // so that global traffic is row-contiguous (8 lanes x 16 B = one 128 B line per row); the epilogue kind is compile-time.
-    const int q = warp & 3, half = (warp - 4) >> 2;      // half = column group 0..3 of this warp
-    const uint32_t stage = smem_u32(smem + L::EPI_OFFSET + (warp - 4) * (32 * 128));
-    const int c4 = lane & 7, rsub = lane >> 3;
-    // Two loop forms. The gelu-grad kind software-pipelines its global operand (the saved pre-activation) one chunk ahead in a
-    // second 16-register buffer; the other kinds keep the single-chunk loop (pipelining the 32-register residual operand, or
-    // merely restructuring the operand-free kinds, measured slower in r1p).
-    if constexpr (EPI == EPI_GELUGRAD_BF16) {
+    // ===== epilogue: 8 warps. Warp w reads TMEM lanes 32*(w%4) .. +31 (one accumulator row per lane) and owns the column
+    // groups half, half+2, ... (half = (w-4)/4) of every tile of this CTA.
+    const int ew = warp - 4, q = warp & 3, half = ew >> 2;
+    const uint32_t ring = smem_u32(smem + L::EPI_OFFSET + ew * (NBUF * EPI_TILE_BYTES));
+    if constexpr (EPI == EPI_UNPATCH) {
+      // ---- patch-embed data gradient: the NCHW destination of a 32-row tile is 32 scattered 128-byte segments (one per patch),
+      // not a TMA box: 32x32 fp32 chunks are transposed through one ring tile and stored row-contiguously by the lanes.
+      const int c4 = lane & 7, rsub = lane >> 3;
       uint32_t tile_iter = 0;
-      WorkIter wi; wi.init(epi.sk, tile0, tile_step, num_tiles, k_blocks);
-      // Global operands of the fused epilogue (the fp32 residual / the saved pre-activation) are software-pipelined one 32-column
-      // chunk ahead, across tile boundaries as well: fetched right before use they cost a full HBM round trip per chunk (ncu r1l:
-      // 28 % of the gelu-grad kernel's stall samples sat on the first use of these registers).
-      constexpr int CSTEP = GEMM_EPI_WARPS / 4, NCH = (BN / 32) / CSTEP;          // chunks per warp per tile (even)
-      constexpr int CU = 2;
-      static_assert(NCH % 2 == 0, "the operand double buffer assumes an even chunk count");
-      float4 res4[2][EPI == EPI_BIAS_RESID ? 8 : 1];
-      uint2 gin[2][EPI == EPI_GELUGRAD_BF16 ? 8 : 1];
-  #define APH_FETCH_OPS(TILE_, C_, BUF_)                                                                                          \
-      do {                                                                                                                        \
-        const int fm_ = ((TILE_) / n_tiles * CG + (int)rank) * GEMM_BM + q * 32;                                                  \
-        const size_t fo_ = (size_t)(fm_ + rsub) * shp.N + ((TILE_) % n_tiles) * BN + (C_) * 32 + 4 * c4;                          \
-        _Pragma("unroll")                                                                                                         \
-        for (int it = 0; it < 8; ++it) {                                                                                          \
-          const bool ok = fm_ + it * 4 + rsub < shp.M;                                                                            \
-          if (EPI == EPI_BIAS_RESID) res4[BUF_][it] = ok ? __ldg(reinterpret_cast<const float4*>(epi.resid + fo_ + (size_t)it * 4 * shp.N)) : make_float4(0.f, 0.f, 0.f, 0.f); \
-          if (EPI == EPI_GELUGRAD_BF16) gin[BUF_][it] = ok ? __ldg(reinterpret_cast<const uint2*>(epi.gelu_in + fo_ + (size_t)it * 4 * shp.N)) : make_uint2(0u, 0u); \
-        }                                                                                                                         \
-      } while (0)
-      int tile, kb0, kb1;
-      bool have = wi.next(tile, kb0, kb1);
-      if (have && !(epi.sk && kb0 > 0)) APH_FETCH_OPS(tile, half, 0);
-      while (have) {
-        int ntile = 0, nkb0 = 0, nkb1 = 0;
-        const bool have_n = wi.next(ntile, nkb0, nkb1);
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_iter) {
         const int m_blk = (tile / n_tiles) * CG + (int)rank, n_blk = tile % n_tiles;
         const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
-        // stream-K roles of this item: park the partial (tile continues from another group's k-blocks) or fix it up
-        const bool p_store = epi.sk && kb0 > 0, p_fix = epi.sk && kb1 < k_blocks;
-        float* ws_st = epi.sk_ws + ((size_t)(tile0 * CG + (int)rank) * GEMM_BM) * BN;             // slot of this group
-        const float* ws_fx = epi.sk_ws + ((size_t)((tile0 + 1) * CG + (int)rank) * GEMM_BM) * BN;  // slot of the next group
-        if (p_fix) {
-          if (lane == 0) { volatile int* f = epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4); const long long t0 = clock64(); while (*f == 0 && clock64() - t0 < 4000000000LL) { } }   /* bounded (~2 s): a protocol bug must fail a test, not hang the GPU */
-          __threadfence();
-          __syncwarp();
-        }
         mbar_wait(&tfull_bar[as], aph_);
         tc_fence_after();
         const int m_base = m_blk * GEMM_BM + q * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-  #pragma unroll 1
-        for (int ci0 = 0; ci0 < NCH; ci0 += CU) {
-  #pragma unroll
-        for (int cu = 0; cu < CU; ++cu) {                  // pairs of chunks: the operand buffer index is a compile-time constant
-          const int ci = ci0 + cu;
-          const int c = half + ci * CSTEP;
-          // next chunk's (or the next tile's first chunk's) operands
-          if (ci + 1 < NCH) { if (!p_store) APH_FETCH_OPS(tile, c + CSTEP, (cu + 1) & 1); }
-          else if (have_n && !(epi.sk && nkb0 > 0)) APH_FETCH_OPS(ntile, half, (cu + 1) & 1);
-          const int col = n_blk * BN + c * 32 + 4 * c4;
-          const size_t off0 = (size_t)(m_base + rsub) * shp.N + col;
-          const size_t step = (size_t)4 * shp.N;
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_wait_ld();
-          if (ci == NCH - 1) {                             // this warp's last read of the accumulator: hand the TMEM stage back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0)); else mbar_arrive(&tempty_bar[as]); }
-          }
-  #pragma unroll
-          for (int i = 0; i < 8; ++i)      // lane = row: write its 32 columns as 8 swizzled 16-byte chunks
-            sts128(stage + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-          __syncwarp();
-          size_t off = off0;
-  #pragma unroll
-          for (int it = 0; it < 8; ++it, off += step) {
-            const int rr = it * 4 + rsub;
-            const int m = m_base + rr;
-            if (m >= shp.M) break;
-            float4 v = lds128(stage + rr * 128 + ((c4 ^ (rr & 7)) << 4));
-            if (p_store || p_fix) {
-              const size_t woff = (size_t)(q * 32 + rr) * BN + c * 32 + 4 * c4;
-              if (p_store) { *reinterpret_cast<float4*>(ws_st + woff) = v; continue; }
-              const float4 w = __ldcg(reinterpret_cast<const float4*>(ws_fx + woff));
-              v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-            }
-            if (EPI == EPI_F32) {
-              if (epi.nostore) { if (v.x == 1.2345e30f) epi.out_f32[0] = v.y; continue; }
-              *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
-            } else if (EPI == EPI_UNPATCH) {
-              const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
-              const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
-              const int ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
-              *reinterpret_cast<float4*>(epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px) = v;
-            } else if (EPI == EPI_BIAS_RESID) {
-              const float4 b = res4[cu][EPI == EPI_BIAS_RESID ? it : 0];
-              v.x += bias4.x + b.x; v.y += bias4.y + b.y; v.z += bias4.z + b.z; v.w += bias4.w + b.w;
-              *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
-            } else {
-              if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
-              if (EPI == EPI_BIAS_GELU) {
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-                uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-                *reinterpret_cast<uint2*>(epi.out_pre + off) = u;
-                v.x = quickgelu(v.x); v.y = quickgelu(v.y); v.z = quickgelu(v.z); v.w = quickgelu(v.w);
-              }
-              if (EPI == EPI_GELUGRAD_BF16) {
-                const uint2 u = gin[cu][EPI == EPI_GELUGRAD_BF16 ? it : 0];
-                const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-                const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-                v.x *= quickgelu_grad(h0.x); v.y *= quickgelu_grad(h0.y); v.z *= quickgelu_grad(h1.x); v.w *= quickgelu_grad(h1.y);
-              }
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-              uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-              *reinterpret_cast<uint2*>(epi.out_bf16 + off) = u;
-            }
-          }
-          __syncwarp();                    // staging tile is reused by this warp's next chunk
-        }
-        }
-        if (p_store) {                     // publish this warp's part of the parked partial
-          __threadfence();
-          __syncwarp();
-          if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + (tile0 * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 1;
-        } else if (p_fix) {                // consumed: re-arm the flag for the next launch
-          __syncwarp();
-          if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 0;
-        }
-        tile = ntile; kb0 = nkb0; kb1 = nkb1; have = have_n; ++tile_iter;
-      }
-  #undef APH_FETCH_OPS
-    } else {
-      uint32_t tile_iter = 0;
-      WorkIter wi; wi.init(epi.sk, tile0, tile_step, num_tiles, k_blocks);
-      int tile, kb0, kb1;
-      for (; wi.next(tile, kb0, kb1); ++tile_iter) {
-        const int m_blk = (tile / n_tiles) * CG + (int)rank, n_blk = tile % n_tiles;
-        const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
-        // stream-K roles of this item: park the partial (tile continues from another group's k-blocks) or fix it up
-        const bool p_store = epi.sk && kb0 > 0, p_fix = epi.sk && kb1 < k_blocks;
-        float* ws_st = epi.sk_ws + ((size_t)(tile0 * CG + (int)rank) * GEMM_BM) * BN;             // slot of this group
-        const float* ws_fx = epi.sk_ws + ((size_t)((tile0 + 1) * CG + (int)rank) * GEMM_BM) * BN;  // slot of the next group
-        if (p_fix) {
-          if (lane == 0) { volatile int* f = epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4); const long long t0 = clock64(); while (*f == 0 && clock64() - t0 < 4000000000LL) { } }   /* bounded (~2 s): a protocol bug must fail a test, not hang the GPU */
-          __threadfence();
-          __syncwarp();
-        }
-        mbar_wait(&tfull_bar[as], aph_);
-        tc_fence_after();
-        const int m_base = m_blk * GEMM_BM + q * 32;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-  #pragma unroll 1
+#pragma unroll 1
         for (int c = half; c < BN / 32; c += GEMM_EPI_WARPS / 4) {
-          // global operands of the fused epilogue are fetched FIRST (8 independent loads in flight per lane): issued inside
-          // the store loop they serialise behind the stores (possible aliasing) and the epilogue becomes load-latency bound
           const int col = n_blk * BN + c * 32 + 4 * c4;
-          const size_t off0 = (size_t)(m_base + rsub) * shp.N + col;
-          const size_t step = (size_t)4 * shp.N;
-          float4 res4[EPI == EPI_BIAS_RESID ? 8 : 1];
-          uint2 gin[EPI == EPI_GELUGRAD_BF16 ? 8 : 1];
-          if ((EPI == EPI_BIAS_RESID || EPI == EPI_GELUGRAD_BF16) && !p_store) {
-  #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const bool ok = m_base + it * 4 + rsub < shp.M;
-              if (EPI == EPI_BIAS_RESID) res4[it] = ok ? __ldg(reinterpret_cast<const float4*>(epi.resid + off0 + it * step)) : make_float4(0.f, 0.f, 0.f, 0.f);
-              if (EPI == EPI_GELUGRAD_BF16) gin[it] = ok ? __ldg(reinterpret_cast<const uint2*>(epi.gelu_in + off0 + it * step)) : make_uint2(0u, 0u);
-            }
-          }
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_wait_ld();
@@ -531,65 +403,134 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0)); else mbar_arrive(&tempty_bar[as]); }
           }
-  #pragma unroll
+#pragma unroll
           for (int i = 0; i < 8; ++i)      // lane = row: write its 32 columns as 8 swizzled 16-byte chunks
-            sts128(stage + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            sts128(ring + lane * 128 + ((i ^ (lane & 7)) << 4), r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
           __syncwarp();
-          size_t off = off0;
-  #pragma unroll
-          for (int it = 0; it < 8; ++it, off += step) {
+          const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
+          const int ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rsub;
             const int m = m_base + rr;
             if (m >= shp.M) break;
-            float4 v = lds128(stage + rr * 128 + ((c4 ^ (rr & 7)) << 4));
-            if (p_store || p_fix) {
-              const size_t woff = (size_t)(q * 32 + rr) * BN + c * 32 + 4 * c4;
-              if (p_store) { *reinterpret_cast<float4*>(ws_st + woff) = v; continue; }
-              const float4 w = __ldcg(reinterpret_cast<const float4*>(ws_fx + woff));
-              v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-            }
-            if (EPI == EPI_F32) {
-              if (epi.nostore) { if (v.x == 1.2345e30f) epi.out_f32[0] = v.y; continue; }
-              *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
-            } else if (EPI == EPI_UNPATCH) {
-              const int p = epi.unpatch_p, g = epi.unpatch_g, R = p * g;
-              const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
-              const int ch = col / (p * p), rem = col - ch * p * p, py = rem / p, px = rem - py * p;
-              *reinterpret_cast<float4*>(epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px) = v;
-            } else if (EPI == EPI_BIAS_RESID) {
-              const float4 b = res4[EPI == EPI_BIAS_RESID ? it : 0];
-              v.x += bias4.x + b.x; v.y += bias4.y + b.y; v.z += bias4.z + b.z; v.w += bias4.w + b.w;
-              *reinterpret_cast<float4*>(epi.out_f32 + off) = v;
-            } else {
-              if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
-              if (EPI == EPI_BIAS_GELU) {
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-                uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-                *reinterpret_cast<uint2*>(epi.out_pre + off) = u;
-                v.x = quickgelu(v.x); v.y = quickgelu(v.y); v.z = quickgelu(v.z); v.w = quickgelu(v.w);
-              }
-              if (EPI == EPI_GELUGRAD_BF16) {
-                const uint2 u = gin[EPI == EPI_GELUGRAD_BF16 ? it : 0];
-                const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-                const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-                v.x *= quickgelu_grad(h0.x); v.y *= quickgelu_grad(h0.y); v.z *= quickgelu_grad(h1.x); v.w *= quickgelu_grad(h1.y);
-              }
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-              uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-              *reinterpret_cast<uint2*>(epi.out_bf16 + off) = u;
-            }
+            const float4 v = lds128(ring + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+            const int s = m / (g * g), pr = m - s * g * g, gy = pr / g, gx = pr - gy * g;
+            *reinterpret_cast<float4*>(epi.out_f32 + (((size_t)s * 3 + ch) * R + gy * p + py) * R + gx * p + px) = v;
           }
           __syncwarp();                    // staging tile is reused by this warp's next chunk
         }
-        if (p_store) {                     // publish this warp's part of the parked partial
-          __threadfence();
-          __syncwarp();
-          if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + (tile0 * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 1;
-        } else if (p_fix) {                // consumed: re-arm the flag for the next launch
-          __syncwarp();
-          if (lane == 0) *reinterpret_cast<volatile int*>(epi.sk_flags + ((tile0 + 1) * CG + (int)rank) * GEMM_EPI_WARPS + (warp - 4)) = 0;
-        }
       }
+    } else {
+      constexpr int CW = E::CW, NI = (BN / CW) / 2;             // items (ring tiles of CW accumulator columns) per warp per tile
+      static_assert(NI >= 1, "tile too narrow for the epilogue split");
+      uint64_t* my_bar = op_bar + ew * NBUF;
+      const int my_tiles = (tile0 < num_tiles) ? (num_tiles - tile0 + tile_step - 1) / tile_step : 0;
+      const int total_items = my_tiles * NI;
+      const uint64_t pol_stream = l2_policy_evict_first();
+      uint32_t slot = 0, ophase = 0;
+      // coordinates of item g: first row of this warp's 32-row slice and first column
+      auto coords = [&](int g, int& m0, int& col0) {
+        const int t = tile0 + (g / NI) * tile_step, i = g - (g / NI) * NI;
+        m0 = ((t / n_tiles) * CG + (int)rank) * GEMM_BM + q * 32;
+        col0 = (t % n_tiles) * BN + (half + 2 * i) * CW;
+      };
+      auto issue_operand = [&](int g) {             // lane 0 only: operand tile of item g -> ring tile g % NBUF
+        int m0, col0; coords(g, m0, col0);
+        if (m0 >= shp.M) return;                    // slice entirely past M: nothing to load (and nothing will be waited for)
+        const int b = g % NBUF;
+        mbar_expect_tx(&my_bar[b], EPI_TILE_BYTES);
+        tma_load_2d_cta(ring + b * EPI_TILE_BYTES, &map_op, &my_bar[b], col0, m0);
+      };
+      if (E::HAS_OP && total_items > 0 && lane == 0) issue_operand(0);
+#pragma unroll 1
+      for (int g = 0; g < total_items; ++g) {
+        const int tile_iter = g / NI, i = g - tile_iter * NI;
+        int m0, col0; coords(g, m0, col0);
+        const bool live = m0 < shp.M;               // warp-uniform
+        const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
+        if (E::HAS_OP) {
+          // next item's operand (possibly the next tile's: it then flies during that tile's main loop). Its ring tile was last
+          // read by the store of item g+1-NBUF: at most NBUF-2 younger stores may still be reading.
+          if (g + 1 < total_items && lane == 0) { bulk_wait_read<NBUF - 2>(); issue_operand(g + 1); }
+        }
+        if (i == 0) { mbar_wait(&tfull_bar[as], aph_); tc_fence_after(); }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + (half + 2 * i) * CW;
+        uint32_t b0, b1 = 0;                        // ring tiles of this item
+        if (E::HAS_OP) {
+          b0 = g % NBUF;
+          if (live) { mbar_wait(&my_bar[b0], (ophase >> b0) & 1u); ophase ^= 1u << b0; }
+        } else {
+          b0 = slot % NBUF; b1 = (slot + 1) % NBUF;
+          if (lane == 0) bulk_wait_read<NBUF - E::NOUT>();      // the ring tiles about to be overwritten are no longer being read
+          __syncwarp();
+        }
+        const uint32_t row0 = ring + b0 * EPI_TILE_BYTES + lane * 128, row1 = ring + b1 * EPI_TILE_BYTES + lane * 128;
+        const int sw = lane & 7;
+#pragma unroll
+        for (int h = 0; h < CW / 32; ++h) {          // 32 accumulator columns at a time
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + h * 32, r);
+          tmem_wait_ld();
+          if (i == NI - 1 && h == CW / 32 - 1) {     // this warp's last read of the accumulator: hand the TMEM stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0)); else mbar_arrive(&tempty_bar[as]); }
+          }
+          const float* bias = epi.bias + col0 + h * 32;
+          if constexpr (!E::OUT16) {
+            // fp32 output: 8 chunks of 4 columns
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float4 v = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
+              const uint32_t a = row0 + ((c ^ sw) << 4);
+              if (EPI == EPI_BIAS_RESID) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
+                const float4 o = lds128(a);
+                v.x += bb.x + o.x; v.y += bb.y + o.y; v.z += bb.z + o.z; v.w += bb.w + o.w;
+              }
+              sts128(a, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+            }
+          } else {
+            // bf16 output: this half fills 16-byte chunks 4h .. 4h+3 of the row (8 columns each)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * c + e]);
+              if (E::HAS_BIAS) {
+                const float4 b0v = __ldg(reinterpret_cast<const float4*>(bias) + 2 * c), b1v = __ldg(reinterpret_cast<const float4*>(bias) + 2 * c + 1);
+                v[0] += b0v.x; v[1] += b0v.y; v[2] += b0v.z; v[3] += b0v.w; v[4] += b1v.x; v[5] += b1v.y; v[6] += b1v.z; v[7] += b1v.w;
+              }
+              const uint32_t off = (uint32_t)(((4 * h + c) ^ sw) << 4);
+              if (EPI == EPI_BIAS_GELU) {
+                sts128(row1 + off, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));      // pre-activation
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = quickgelu(v[e]);
+              }
+              if (EPI == EPI_GELUGRAD_BF16) {
+                const uint4 u = lds128u(row0 + off);
+                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 hh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uu[e]));
+                  v[2 * e] *= quickgelu_grad(hh.x); v[2 * e + 1] *= quickgelu_grad(hh.y);
+                }
+              }
+              sts128(row0 + off, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+          }
+        }
+        fence_proxy_async();                         // generic-proxy writes of the ring tile -> visible to the bulk-tensor store
+        __syncwarp();
+        if (lane == 0 && live) {
+          tma_store_2d(&map_o1, ring + b0 * EPI_TILE_BYTES, col0, m0);
+          bulk_commit();
+          if (E::NOUT == 2) { tma_store_2d_hint(&map_o2, ring + b1 * EPI_TILE_BYTES, col0, m0, pol_stream); bulk_commit(); }   // saved for backward only
+        }
+        slot += E::NOUT;
+      }
+      if (lane == 0) bulk_wait_read<0>();            // shared memory must stay valid until the last store has read it
     }
   }
   __syncwarp();               // single-lane roles rejoin their warp before the (warp-aligned) cluster barrier
@@ -602,6 +543,8 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // 2-D bf16 tensor map: tensor [rows, K] row-major, box [box_rows, 64] with 128B swizzle.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int K, int box_rows);
 int make_tmap_bf16_tokens(CUtensorMap* out, const void* base, int cols, int T, int S, int box_rows);
+// epilogue ring-tile map: tensor [rows, cols] row-major of 2- or 4-byte elements, box 32 rows x 128 bytes, 128B swizzle
+int make_tmap_epi(CUtensorMap* out, const void* base, int rows, int cols, int elem_bytes);
 // Launches the GEMM on `st`. A: [M,K], B: [N,K] device bf16. Requires K % 64 == 0, N % 128 == 0.
 int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st);
 

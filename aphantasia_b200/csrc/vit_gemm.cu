@@ -56,63 +56,62 @@ int make_tmap_bf16_tokens(CUtensorMap* out, const void* base, int cols, int T, i
   return 0;
 }
 
+int make_tmap_epi(CUtensorMap* out, const void* base, int rows, int cols, int elem_bytes) {
+  EncodeTiledFn enc = get_encode();
+  APH_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  APH_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "epilogue tensor map: element size %d", elem_bytes);
+  APH_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ((size_t)cols * elem_bytes) % 16 == 0, "epilogue tensor map: base/stride not 16-byte aligned");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * elem_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), 32u};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+                         gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  APH_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (epilogue) failed: CUresult %d (rows=%d cols=%d elem=%d)", (int)r, rows, cols, elem_bytes);
+  return 0;
+}
+
 // ---- optional per-launch event timing (bench.py's roofline: the GEMM kernel's real time inside a step)
 static bool g_prof = false;
 bool gemm_profiling_on() { return g_prof; }
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev;
 static std::vector<double> g_prof_flops;
 
-// stream-K scratch (one in-flight GEMM at a time: all launches of this library go to the caller's single stream)
-static float* g_sk_ws = nullptr;
-static int* g_sk_flags = nullptr;
-
-static int sk_prepare() {
-  if (g_sk_ws) return 0;
-  APH_CUDA_OK(cudaMalloc(&g_sk_ws, (size_t)kNumSMs * GEMM_BM * 256 * sizeof(float)));
-  APH_CUDA_OK(cudaMalloc(&g_sk_flags, (size_t)(kNumSMs + 2) * GEMM_EPI_WARPS * sizeof(int)));
-  APH_CUDA_OK(cudaMemset(g_sk_flags, 0, (size_t)(kNumSMs + 2) * GEMM_EPI_WARPS * sizeof(int)));
-  return 0;
-}
-
 // launches per (tile variant, epilogue kind): variant 0 = 128x128 single CTA, 1 = 128x256 single CTA, 2 = 256x256 CTA pair.
 // Read by the tests to prove which kernel a shape really ran (aph_gemm_variant_launches).
 static std::atomic<long long> g_variant_launches[3][EPI_KINDS];
 
-template <int BN, int STAGES, int EPI, int CG = 1>
-static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi_in, cudaStream_t st) {
-  using L = GemmSmem<BN, STAGES, CG>;
-  GemmEpi epi = epi_in;
+template <int BN, int EPI, int CG>
+static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st) {
+  using E = EpiTraits<EPI>;
+  constexpr int STAGES = E::STAGES, NBUF = E::NBUF;
+  using L = GemmSmem<BN, STAGES, CG, NBUF>;
+  static_assert(L::TOTAL <= 227 * 1024, "GEMM shared-memory budget");
   g_variant_launches[CG == 2 ? 2 : (BN == 256 ? 1 : 0)][EPI].fetch_add(1, std::memory_order_relaxed);
   static bool configured = false;
   if (!configured) {
-    APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES, EPI, CG, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo1, mo2, mop;
   if (int e = make_tmap_bf16(&ma, A, shp.M, shp.K, GEMM_BM)) return e;
   if (int e = make_tmap_bf16(&mb, B, shp.N, shp.K, BN / CG)) return e;
+  mo1 = ma; mo2 = ma; mop = ma;                       // placeholders for the maps a kind does not use
+  if (EPI != EPI_UNPATCH) {
+    if (E::OUT16) { if (int e = make_tmap_epi(&mo1, epi.out_bf16, shp.M, shp.N, 2)) return e; }
+    else { if (int e = make_tmap_epi(&mo1, epi.out_f32, shp.M, shp.N, 4)) return e; }
+  }
+  if (EPI == EPI_BIAS_GELU) { if (int e = make_tmap_epi(&mo2, epi.out_pre, shp.M, shp.N, 2)) return e; }
+  if (EPI == EPI_BIAS_RESID) { if (int e = make_tmap_epi(&mop, epi.resid, shp.M, shp.N, 4)) return e; }
+  if (EPI == EPI_GELUGRAD_BF16) { if (int e = make_tmap_epi(&mop, epi.gelu_in, shp.M, shp.N, 2)) return e; }
   const int tiles = ((shp.M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * (shp.N / BN);
   const int slots = kNumSMs / CG;
   const int groups = tiles < slots ? tiles : slots;
   const int grid = CG * groups;
-  {
-    // stream-K (opt-in, APH_GEMM_STREAMK=1): units = tiles x k-blocks split evenly over the groups, split tiles fixed up through
-    // a parked fp32 partial. Correct (tests pass with it on) but MEASURED SLOWER at the ViT-B shapes (profiles/README.md): with
-    // K = 768 a tile's epilogue costs as much as its main loop, so the extra partial-store / fix-up epilogue per group outweighs
-    // the k-blocks saved by removing the ragged last round (9500x768x768: 31.4 vs 19.1 us; 9500x3072x768: 67.6 vs 47.7 us).
-    static int sk_on = -1;
-    if (sk_on < 0) { const char* e = getenv("APH_GEMM_STREAMK"); sk_on = (e && e[0] == '1') ? 1 : 0; }
-    const int kb = shp.K / GEMM_BK;
-    const long long units = (long long)tiles * kb;
-    const long long cost_static = (long long)((tiles + groups - 1) / groups) * kb, cost_sk = (units + groups - 1) / groups;
-    if (sk_on && tiles > groups && units / groups >= kb && cost_sk + 3 < cost_static) {
-      if (int e = sk_prepare()) return e;
-      epi.sk = 1; epi.sk_ws = g_sk_ws; epi.sk_flags = g_sk_flags;
-    }
-  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
-  APH_CUDA_OK(launch_k(k_gemm_bf16_tn<BN, STAGES, EPI, CG>, dim3(grid), dim3(GEMM_THREADS), (size_t)L::TOTAL, st, CG, ma, mb, shp, epi));
+  APH_CUDA_OK(launch_k(k_gemm_bf16_tn<BN, STAGES, EPI, CG, NBUF>, dim3(grid), dim3(GEMM_THREADS), (size_t)L::TOTAL, st, CG, ma, mb, mo1, mo2, mop, shp, epi));
   APH_LAUNCH_OK();
   if (g_prof) { cudaEventRecord(e1, st); g_prof_ev.emplace_back(e0, e1); g_prof_flops.push_back(2.0 * shp.M * shp.N * shp.K); }
   return 0;
@@ -122,15 +121,6 @@ int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi,
   APH_REQUIRE(A && B && shp.M > 0, "gemm: null operand or empty M");
   APH_REQUIRE(shp.K % GEMM_BK == 0 && shp.K > 0, "gemm: K=%d must be a positive multiple of %d", shp.K, GEMM_BK);
   APH_REQUIRE(shp.N % 128 == 0 && shp.N > 0, "gemm: N=%d must be a positive multiple of 128", shp.N);
-  // tile width: APH_GEMM_BN=128|256 forces one; default picks 256-wide tiles when N allows it and the grid still fills
-  static int forced = -1;
-  if (forced < 0) { const char* e = getenv("APH_GEMM_BN"); forced = e ? atoi(e) : 0; }
-  bool wide = (shp.N % 256 == 0);
-  if (forced == 128) wide = false;
-  else if (forced != 256 && wide) {
-    const int mt = (shp.M + GEMM_BM - 1) / GEMM_BM;
-    wide = mt * (shp.N / 256) >= kNumSMs;          // small problems keep the finer 128-wide tiling
-  }
   // map the requested fusion onto one of the compiled epilogue kinds
   int kind = -1;
   const bool b = epi.bias, r = epi.resid, gi = epi.gelu_in, f = epi.out_f32, h = epi.out_bf16, pre = epi.out_pre, act = epi.act == 1, un = epi.unpatch_p > 0;
@@ -142,12 +132,12 @@ int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi,
   else if (f && !h && b && r && !gi && !pre && !act) kind = EPI_BIAS_RESID;
   else if (h && !f && !b && !r && gi && !pre && !act) kind = EPI_GELUGRAD_BF16;
   APH_REQUIRE(kind >= 0, "gemm: unsupported epilogue combination");
-  // CTA-pair tiles (cta_group::2, 256 x 256 accumulator per pair, B tile split across the pair) are the default for large
-  // problems: measured +3 % steps/s at C2 (profiles/README.md). APH_GEMM_2CTA=0 forces single-CTA tiles.
+  // CTA-pair tiles (cta_group::2, 256 x 256 accumulator per pair, B tile split across the pair) for problems that fill the
+  // 74 SM pairs; smaller problems keep the finer 128 x 128 single-CTA tiling. APH_GEMM_2CTA=0 forces single-CTA tiles.
   static int pair = -1;
   if (pair < 0) { const char* e = getenv("APH_GEMM_2CTA"); pair = (e && e[0] == '0') ? 0 : 1; }
-  const bool use_pair = pair && wide && ((shp.M + 255) / 256) * (shp.N / 256) >= kNumSMs / 2;
-#define APH_GEMM_CASE(K) case K: return use_pair ? launch_cfg<256, 6, K, 2>(A, B, shp, epi, st) : (wide ? launch_cfg<256, 4, K>(A, B, shp, epi, st) : launch_cfg<128, 6, K>(A, B, shp, epi, st));
+  const bool use_pair = pair && shp.N % 256 == 0 && ((shp.M + 255) / 256) * (shp.N / 256) >= kNumSMs / 2;
+#define APH_GEMM_CASE(K) case K: return use_pair ? launch_cfg<256, K, 2>(A, B, shp, epi, st) : launch_cfg<128, K, 1>(A, B, shp, epi, st);
   switch (kind) {
     APH_GEMM_CASE(EPI_F32) APH_GEMM_CASE(EPI_BF16) APH_GEMM_CASE(EPI_BIAS_BF16) APH_GEMM_CASE(EPI_BIAS_GELU)
     APH_GEMM_CASE(EPI_BIAS_RESID) APH_GEMM_CASE(EPI_GELUGRAD_BF16) APH_GEMM_CASE(EPI_UNPATCH)
@@ -164,7 +154,6 @@ extern "C" int aph_gemm_bf16_tn(const void* A, const void* B, float* C, int M, i
   APH_REQUIRE(C != nullptr, "aph_gemm_bf16_tn: null output");
   GemmEpi epi;
   epi.out_f32 = C;
-  { const char* e = getenv("APH_GEMM_NOSTORE"); epi.nostore = (e && e[0] == '1') ? 1 : 0; }
   return launch_gemm(A, B, GemmShape{M, N, K}, epi, (cudaStream_t)stream);
 }
 

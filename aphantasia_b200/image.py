@@ -10,7 +10,7 @@ import os
 import numpy as np
 import torch
 
-from . import _dist
+from . import _dist, _pool
 from ._lib import check, lib, require_cuda, stream_ptr
 
 
@@ -37,9 +37,9 @@ class _SynthFFT(torch.autograd.Function):
         require_cuda(params, 'spectrum parameters')
         h, w = gen.h, gen.w
         p = params.detach().contiguous().float()
-        x_raw = torch.empty(3, h, w, device=p.device, dtype=torch.float32)
-        out = torch.empty(1, 3, h, w, device=p.device, dtype=torch.float32)
-        stats = torch.empty(4, device=p.device, dtype=torch.float64)
+        x_raw = _pool.empty((3, h, w))
+        out = _pool.empty((1, 3, h, w))
+        stats = _pool.empty((4,), torch.float64)
         mode, sh = 0, None
         if shift is not None:
             sh = shift.detach().to(p.device, torch.float32).contiguous()
@@ -72,7 +72,7 @@ class _SynthFFT(torch.autograd.Function):
                                                ctx.contrast, ctx.colmat, ctx.sigmoid, None, p.data_ptr(), m.data_ptr(), v.data_ptr(),
                                                lr, b1, b2, eps, step, stream_ptr()), 'aph_synth_fft_bwd_adam')
             return None, None, None, None, None, None
-        gp = torch.empty(1, 3, gen.h, gen.wh, 2, device=g.device, dtype=torch.float32)
+        gp = _pool.empty((1, 3, gen.h, gen.wh, 2))
         check(lib().aph_synth_fft_bwd(gen.plan, g.data_ptr(), out.data_ptr(), x_raw.data_ptr(), stats.data_ptr(), gen.scale.data_ptr(),
                                       ctx.contrast, ctx.colmat, ctx.sigmoid, gp.data_ptr(), stream_ptr()), 'aph_synth_fft_bwd')
         return gp, None, None, None, None, None

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import _dist, _rng, _trace
+from . import _dist, _pool, _rng, _trace
 from ._lib import check, lib, require_cuda, stream_ptr
 
 
@@ -20,7 +20,7 @@ class _SliceImgs(torch.autograd.Function):
     def forward(ctx, canvas, table_dev, meta):
         H, W, pad_top, pad_left, S, size, kind, scale = meta
         x = canvas.detach().contiguous().float()
-        out = torch.empty(S, 3, size, size, device=x.device, dtype=torch.float32)
+        out = _pool.empty((S, 3, size, size))
         check(lib().aph_sample_fwd(x.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, out.data_ptr(),
                                    stream_ptr()), 'aph_sample_fwd')
         ctx.meta = meta
@@ -32,7 +32,7 @@ class _SliceImgs(torch.autograd.Function):
         table_dev, = ctx.saved_tensors
         H, W, pad_top, pad_left, S, size, kind, scale = ctx.meta
         g = grad_out.contiguous().float()
-        gc = torch.empty(1, 3, H, W, device=g.device, dtype=torch.float32)
+        gc = _pool.empty((1, 3, H, W))
         check(lib().aph_sample_bwd(g.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, gc.data_ptr(),
                                    stream_ptr()), 'aph_sample_bwd')
         if _dist.world() > 1:
@@ -269,14 +269,27 @@ def _drain_saves():
         _pending.pop(0).result()
 
 
+def _imsave(path, img):
+    try:
+        from imageio import imsave
+    except ImportError:                 # imageio absent and dropin/ not on the path: same PIL encoder dropin/imageio wraps
+        from PIL import Image
+        Image.fromarray(img).save(path, **({'quality': 95} if path.lower().endswith(('.jpg', '.jpeg')) else {}))
+        return
+    imsave(path, img)
+
+
 def _encode_save(fname, chw):
-    from imageio import imsave
-    img = np.transpose(chw, (1, 2, 0))
+    # utils.py:98-100: transpose to HWC, clip(img*255, 0, 255) -> uint8. Done channel-major on contiguous memory, then ONE
+    # transposing uint8 copy: the encoder gets a C-contiguous HWC buffer (a strided view costs PIL an extra 10 ms tobytes()).
+    x = np.multiply(chw, np.float32(255.))
+    np.clip(x, 0, 255, out=x)
+    img = np.ascontiguousarray(np.transpose(x.astype(np.uint8), (1, 2, 0)))
     # encode under a temporary name in the same directory, then rename: a reader of the directory (ffmpeg, img_list) never
     # sees a half-written frame. The temporary keeps the extension so the encoder still picks the format from it.
     base, ext = os.path.splitext(fname)
     tmp = '%s.tmp%d%s' % (base, os.getpid(), ext)
-    imsave(tmp, np.clip(img * 255, 0, 255).astype(np.uint8))          # utils.py:98-100
+    _imsave(tmp, img)
     os.replace(tmp, fname)
 
 
