@@ -10,7 +10,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import _dist, _pool, _rng, _trace
+from . import _dist, _rng, _trace
+from . import _pool as _tpool
 from ._lib import check, lib, require_cuda, stream_ptr
 
 
@@ -20,7 +21,7 @@ class _SliceImgs(torch.autograd.Function):
     def forward(ctx, canvas, table_dev, meta):
         H, W, pad_top, pad_left, S, size, kind, scale = meta
         x = canvas.detach().contiguous().float()
-        out = _pool.empty((S, 3, size, size))
+        out = _tpool.empty((S, 3, size, size))
         check(lib().aph_sample_fwd(x.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, out.data_ptr(),
                                    stream_ptr()), 'aph_sample_fwd')
         ctx.meta = meta
@@ -32,7 +33,7 @@ class _SliceImgs(torch.autograd.Function):
         table_dev, = ctx.saved_tensors
         H, W, pad_top, pad_left, S, size, kind, scale = ctx.meta
         g = grad_out.contiguous().float()
-        gc = _pool.empty((1, 3, H, W))
+        gc = _tpool.empty((1, 3, H, W))
         check(lib().aph_sample_bwd(g.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, gc.data_ptr(),
                                    stream_ptr()), 'aph_sample_bwd')
         if _dist.world() > 1:
