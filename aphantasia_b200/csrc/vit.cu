@@ -8,6 +8,7 @@
 // LayerNorm backward can recompute x-hat. No weight gradients (the reference computes and discards them).
 #include "vit_ops.cuh"
 #include "vit_attn_tc.cuh"
+#include "vit_attn_umma.cuh"
 #include <stdlib.h>
 #include <string>
 #include <vector>
@@ -56,7 +57,7 @@ struct VitImpl {
   float* dx = nullptr;           // [M, D]
   bf16* dx_bf = nullptr;         // [M, D]
   bf16* dh = nullptr;            // [M, 4D]
-  float* d_ln = nullptr;         // [M, D]
+  bf16* d_ln = nullptr;          // [M, D] gradient entering a LayerNorm backward (bf16: it is the output of a bf16-operand GEMM and is consumed once)
   bf16* d_attn = nullptr;        // [M, D]
   bf16* d_qkv = nullptr;         // [M, 3D]
   bf16* d_tok = nullptr;         // [S*g*g, D]
@@ -179,6 +180,13 @@ static inline int rows_grid(int rows) { return (rows * 32 + 255) / 256; }
 static bool attn_simt() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("APH_ATTN_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+// APH_ATTN_UMMA=0 falls back to the mma.sync forward for T <= 64 (default: the tcgen05 / TMEM kernel of vit_attn_umma.cuh)
+static bool attn_umma() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("APH_ATTN_UMMA"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
 
@@ -342,6 +350,7 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
     { GemmEpi ep; ep.bias = w.b_qkv; ep.out_bf16 = v->qkv[l];
       if ((e = launch_gemm(v->ln_out, w.w_qkv, GemmShape{M, 3 * D, D}, ep, st))) return e; }
     if (attn_simt()) { k_attn_fwd<<<S * H, 256, attn_fwd_smem(T), st>>>(v->qkv[l], v->attn_out, T, D, H); APH_LAUNCH_OK(); }
+    else if (T <= 64 && attn_umma()) { if ((e = attn_fwd_umma_launch(v->qkv[l], v->attn_out, S, T, D, H, st))) return e; }
     else if ((e = attn_dispatch(true, v->qkv[l], nullptr, v->attn_out, S, T, D, H, st))) return e;
     { GemmEpi ep; ep.bias = w.b_o; ep.resid = x_in; ep.out_f32 = x_mid;
       if ((e = launch_gemm(v->attn_out, w.w_o, GemmShape{M, D, D}, ep, st))) return e; }
@@ -401,18 +410,18 @@ extern "C" int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* gr
     // MLP branch: dh = (dx . W_proj) * gelu'(h); d_ln2 = dh . W_fc
     { GemmEpi ep; ep.gelu_in = v->h_pre[l]; ep.out_bf16 = v->dh;
       if ((e = launch_gemm(v->dx_bf, w.w_proj_t, GemmShape{M, 4 * D, D}, ep, st))) return e; }
-    { GemmEpi ep; ep.out_f32 = v->d_ln;
+    { GemmEpi ep; ep.out_bf16 = v->d_ln;
       if ((e = launch_gemm(v->dh, w.w_fc_t, GemmShape{M, D, 4 * D}, ep, st))) return e; }
-    NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_bwd<NCH>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, v->d_ln, x_mid, mean2, rstd2, w.ln2_w, v->dx, v->dx_bf, M, T, D, 0, 1)));
+    NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_bwd<NCH, bf16>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, v->d_ln, x_mid, mean2, rstd2, w.ln2_w, v->dx, v->dx_bf, M, T, D, 0, 1)));
     APH_LAUNCH_OK();
     // attention branch: d_attn = dx . W_o; (dq,dk,dv) = attn'(...); d_ln1 = d_qkv . W_qkv
     { GemmEpi ep; ep.out_bf16 = v->d_attn;
       if ((e = launch_gemm(v->dx_bf, w.w_o_t, GemmShape{M, D, D}, ep, st))) return e; }
     if (attn_simt()) { k_attn_bwd<<<S * H, 256, attn_bwd_smem(T), st>>>(v->qkv[l], v->d_attn, v->d_qkv, T, D, H); APH_LAUNCH_OK(); }
     else if ((e = attn_dispatch(false, v->qkv[l], v->d_attn, v->d_qkv, S, T, D, H, st))) return e;
-    { GemmEpi ep; ep.out_f32 = v->d_ln;
+    { GemmEpi ep; ep.out_bf16 = v->d_ln;
       if ((e = launch_gemm(v->d_qkv, w.w_qkv_t, GemmShape{M, D, 3 * D}, ep, st))) return e; }
-    NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_bwd<NCH>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, v->d_ln, x_in, mean1, rstd1, w.ln1_w, v->dx, v->dx_bf, M, T, D, 0, 1)));
+    NCH_DISPATCH(D, APH_CUDA_OK(launch_k(k_ln_bwd<NCH, bf16>, dim3(rows_grid(M)), dim3(256), (size_t)0, st, 1, v->d_ln, x_in, mean1, rstd1, w.ln1_w, v->dx, v->dx_bf, M, T, D, 0, 1)));
     APH_LAUNCH_OK();
   }
   // ln_pre backward (cls rows dropped) and patch-embed data gradient scattered back to NCHW

@@ -63,6 +63,16 @@ __device__ __forceinline__ void load_row(const float* __restrict__ row, float (&
     v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = a.z; v[4 * k + 3] = a.w;
   }
 }
+// bf16 row -> fp32 registers (same lane ownership as load_row: chunk k holds elements (k*32 + lane)*4 .. +3)
+template <int N>
+__device__ __forceinline__ void load_row(const bf16* __restrict__ row, float (&v)[N], int lane) {
+#pragma unroll
+  for (int k = 0; k < N / 4; ++k) {
+    const uint2 u = *reinterpret_cast<const uint2*>(row + (k * 32 + lane) * 4);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = b.x; v[4 * k + 3] = b.y;
+  }
+}
 template <int N>
 __device__ __forceinline__ void store_row_f32(float* __restrict__ row, const float (&v)[N], int lane) {
 #pragma unroll
@@ -146,8 +156,8 @@ __device__ __forceinline__ void ln_bwd_row(float (&v)[N], const float (&xv)[N], 
 // mode 0: all rows: dx[row] (+)= LNbwd(dy[row]); writes dx (fp32) and dx_bf16.        (ln_1 / ln_2)
 // mode 1: ln_post: dy has S rows (cls only); dx[s*T] = LNbwd, other rows were zeroed by the caller.
 // mode 2: ln_pre : dy = dx itself (all rows); writes only non-cls rows as bf16 into dtok [S*(T-1), D].
-template <int NCH>
-__global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+template <int NCH, typename DY = float>
+__global__ void __launch_bounds__(256) k_ln_bwd(const DY* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                 float* __restrict__ dx, bf16* __restrict__ dx_bf16, int rows, int T, int D,
                                                 int mode, int accumulate) {
