@@ -119,6 +119,9 @@ __device__ __forceinline__ float stageB(const float* __restrict__ A, const CropP
   return A[y * size + x];
 }
 
+// the rotate stage is the identity resampling (angle 0: theta = [[1, 0], [0, 1]])
+__device__ __forceinline__ bool identity_rot(const CropParams& p) { return p.r00 == 1.f && p.r01 == 0.f && p.r10 == 0.f && p.r11 == 1.f; }
+
 __constant__ float c_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
 __constant__ float c_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
@@ -200,6 +203,14 @@ k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pa
   const float inv_sd = 1.f / c_std[ch], shift = -c_mean[ch] * inv_sd;
   if (kind == APH_TF_FAST) {
     if (p.flags & APH_FLAG_PERSP) fwd_compose<true>(A, p, size, warp, lane, nwarps, inv_sd, shift, o);
+    else if (identity_rot(p)) {
+      // angle 0 (26 % of the draws, transforms.py:168) without a perspective hit: the rotate stage resamples every pixel at its own
+      // centre (bilinear weights (1, 0, 0, 0) up to 1e-6 round-off, coverage 1), so stages 2-5 reduce to erase + normalise.
+      for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int y = idx / size, x = idx - y * size;
+        o[idx] = erased(p, y, x) ? shift : fmaf(A[idx], inv_sd, shift);
+      }
+    }
     else fwd_compose<false>(A, p, size, warp, lane, nwarps, inv_sd, shift, o);
   } else {
     const float a = (kind != APH_TF_NONE) ? inv_sd : 1.f, b = (kind != APH_TF_NONE) ? shift : 0.f;
@@ -383,7 +394,13 @@ k_sample_bwd_cas(const float* __restrict__ grad_out, int H, int W, int pad_top, 
   const TapTables tt = build_taps(gA + ((n + 3) & ~3), p, size, H, W, pad_top, pad_left, scale);
   float* strip = gA + ((n + 3) & ~3) + 16 * size + warp * STRIP;
   for (int x = lane; x < STRIP; x += 32) strip[x] = 0.f;           // the strip is re-zeroed as it is drained below
-  if (kind == APH_TF_FAST) {
+  if (kind == APH_TF_FAST && !(p.flags & APH_FLAG_PERSP) && identity_rot(p)) {
+    // adjoint of the angle-0 fast path of the forward: erase mask + 1/std, no scatter
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+      const int y = idx / size, x = idx - y * size;
+      gA[idx] = erased(p, y, x) ? 0.f : go[idx] * inv_sd;
+    }
+  } else if (kind == APH_TF_FAST) {
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) gA[idx] = 0.f;
     __syncthreads();
     if (p.flags & APH_FLAG_PERSP) bwd_compose<true, false>(gA, go, p, size, warp, lane, nwarps, inv_sd);

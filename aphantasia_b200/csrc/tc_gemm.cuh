@@ -297,7 +297,11 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int m_tiles = (shp.M + GEMM_BM * CG - 1) / (GEMM_BM * CG), n_tiles = shp.N / BN;
   const int num_tiles = m_tiles * n_tiles, k_blocks = shp.K / GEMM_BK;
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
-  constexpr uint32_t TMEM_COLS = 2 * BN;
+  // BN = 384 ("one-wave" tiles for the N = 768 GEMMs: 37 x 2 pair tiles of 256 x 384 on the 74 SM pairs) holds ONE accumulator
+  // stage (384 of the 512 TMEM columns); the narrower tiles double-buffer theirs so a tile's epilogue overlaps the next main loop
+  constexpr int ACC = (BN == 384) ? 1 : 2;
+  constexpr uint32_t TMEM_COLS = (BN == 384) ? 512 : 2 * BN;
+  static_assert(BN == 128 || BN == 256 || (BN == 384 && CG == 2), "tile widths: 128, 256, or 384 (CTA pair only)");
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
@@ -334,7 +338,15 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[s]), 0);
             if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES); else mbar_arrive_cluster(lead_full);
             tma_load_2d_2sm(sa, &map_a, lead_full, kb * GEMM_BK, m_blk * GEMM_BM);
-            tma_load_2d_2sm(sa + L::A_BYTES, &map_b, lead_full, kb * GEMM_BK, n_blk * BN + (int)rank * (BN / 2));
+            if (BN == 384) {
+              // this CTA's half of the N = 256 instruction (128 rows of B) followed by its half of the N = 128 one (64 rows); 64-row boxes
+              const int n0 = n_blk * BN;
+              tma_load_2d_2sm(sa + L::A_BYTES, &map_b, lead_full, kb * GEMM_BK, n0 + (int)rank * 128);
+              tma_load_2d_2sm(sa + L::A_BYTES + 64 * 128, &map_b, lead_full, kb * GEMM_BK, n0 + (int)rank * 128 + 64);
+              tma_load_2d_2sm(sa + L::A_BYTES + 128 * 128, &map_b, lead_full, kb * GEMM_BK, n0 + 256 + (int)rank * 64);
+            } else {
+              tma_load_2d_2sm(sa + L::A_BYTES, &map_b, lead_full, kb * GEMM_BK, n_blk * BN + (int)rank * (BN / 2));
+            }
           } else {
             mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
             tma_load_2d(sa, &map_a, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
@@ -346,10 +358,11 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       // ===== MMA issuer (the leader CTA issues for the pair when CG = 2)
-      constexpr uint32_t idesc = make_idesc_bf16(BN, GEMM_BM * CG);
+      constexpr uint32_t idesc = make_idesc_bf16(BN == 384 ? 256 : BN, GEMM_BM * CG);
+      constexpr uint32_t idesc_b = make_idesc_bf16(128, GEMM_BM * CG);        // second instruction of a 384-wide tile
       uint32_t it = 0, tile_iter = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_iter) {
-        const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
+        const uint32_t as = tile_iter % ACC, aph_ = (tile_iter / ACC) & 1;
         mbar_wait(&tempty_bar[as], aph_ ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -364,6 +377,8 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (>>4) address field
             if (CG == 2) umma_f16_cg2(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
             else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            if (BN == 384)      // columns 256..383: B rows 128.. of this stage (16 KB further: +1024 in the >>4 address field)
+              umma_f16_cg2(tmem_d + 256, da + (uint64_t)(2 * k), db + (uint64_t)(1024 + 2 * k), idesc_b, (kb | k) != 0);
           }
           if (CG == 2) {
             umma_commit_mc(&empty_bar[s], 0b11);                            // both CTAs' smem stages are free
@@ -387,7 +402,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t tile_iter = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_iter) {
         const int m_blk = (tile / n_tiles) * CG + (int)rank, n_blk = tile % n_tiles;
-        const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
+        const uint32_t as = tile_iter % ACC, aph_ = (tile_iter / ACC) & 1;
         mbar_wait(&tfull_bar[as], aph_);
         tc_fence_after();
         const int m_base = m_blk * GEMM_BM + q * 32;
@@ -448,7 +463,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int tile_iter = g / NI, i = g - tile_iter * NI;
         int m0, col0; coords(g, m0, col0);
         const bool live = m0 < shp.M;               // warp-uniform
-        const uint32_t as = tile_iter & 1, aph_ = (tile_iter >> 1) & 1;
+        const uint32_t as = tile_iter % ACC, aph_ = (tile_iter / ACC) & 1;
         if (E::HAS_OP) {
           // next item's operand (possibly the next tile's: it then flies during that tile's main loop). Its ring tile was last
           // read by the store of item g+1-NBUF: at most NBUF-2 younger stores may still be reading.

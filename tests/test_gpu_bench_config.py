@@ -49,6 +49,9 @@ def _quickgelu_grad(x):
 @pytest.mark.parametrize('kind,M,N,K', [
     ('f32', 9500, 768, 3072),            # d fc1 (ViT-B/32 data-gradient)
     ('bf16', 9500, 768, 768),            # d out_proj
+    ('bf16', 9500, 768, 3072),           # d fc1 (bf16 gradient into the LayerNorm backward)
+    ('bf16', 9500, 768, 2304),           # d qkv
+    ('bf16', 9259, 768, 768),            # ViT-B/16 batch: 36 x 2 one-wave tiles + 43 remainder rows
     ('bias_bf16', 9500, 2304, 768),      # qkv
     ('bias_gelu', 9500, 3072, 768),      # fc1 + QuickGELU (saves the pre-activation)
     ('bias_resid', 9500, 768, 3072),     # fc2 + residual
@@ -70,7 +73,8 @@ def test_pair_gemm_epilogue_kinds_at_bench_size(L, kind, M, N, K):
     resid = torch.randn(M, N, device=dev)
     hpre = torch.randn(M, N, device=dev).bfloat16()
     nul = None
-    before = lib.aph_gemm_variant_launches(2, EPI[kind])
+    pair_launches = lambda: lib.aph_gemm_variant_launches(2, EPI[kind]) + lib.aph_gemm_variant_launches(3, EPI[kind])     # 256x256 pair or 256x384 one-wave pair
+    before = pair_launches()
     st = L.stream_ptr()
     if kind == 'f32':
         out = torch.full((M, N), float('nan'), device=dev)
@@ -104,7 +108,9 @@ def test_pair_gemm_epilogue_kinds_at_bench_size(L, kind, M, N, K):
         ref = acc.reshape(S, g, g, 3, p, p).permute(0, 3, 1, 4, 2, 5).reshape(S, 3, 224, 224)
         checks = [(out, ref, 1e-5)]
     torch.cuda.synchronize()
-    assert lib.aph_gemm_variant_launches(2, EPI[kind]) == before + 1, 'this shape did not run the cta_group::2 pair kernel'
+    assert pair_launches() == before + 1, 'this shape did not run a cta_group::2 pair kernel'
+    if kind in ('bf16', 'bias_resid') and N == 768:
+        assert lib.aph_gemm_variant_launches(3, EPI[kind]) >= 1, 'N = 768 at this M should take the one-wave 256x384 tiles (+ remainder-row kernel)'
     for got, want, tol in checks:
         assert torch.isfinite(got).all()
         assert _rel(got, want) < tol, (kind, M, N, K, _rel(got, want))
@@ -130,7 +136,8 @@ def test_vit_at_bench_batch_vs_oracle_incl_graph_replay(L, patch, S):
     (eo * cot).sum().backward()
     xc, gc = x.cuda(), cot.cuda()
     emb = torch.empty(S, 512, device='cuda'); gx = torch.empty(S, 3, 224, 224, device='cuda')
-    pair_before = lib.aph_gemm_variant_launches(2, -1)
+    pairs = lambda: lib.aph_gemm_variant_launches(2, -1) + lib.aph_gemm_variant_launches(3, -1)
+    pair_before = pairs()
     errs = []
     for it in range(3):
         emb.fill_(float('nan')); gx.fill_(float('nan'))
@@ -138,7 +145,7 @@ def test_vit_at_bench_batch_vs_oracle_incl_graph_replay(L, patch, S):
         L.check(lib.aph_vit_bwd(vis.handle, gc.data_ptr(), S, gx.data_ptr(), L.stream_ptr()), 'vit_bwd')
         torch.cuda.synchronize()
         if it == 0:
-            assert lib.aph_gemm_variant_launches(2, -1) - pair_before >= 90, 'the cta_group::2 pair kernels were not selected at this batch'
+            assert pairs() - pair_before >= 90, 'the cta_group::2 pair kernels were not selected at this batch'
         errs.append((_rel(emb, eo), _rel(gx, xo.grad)))
     print('vit B/%d S=%d: rel err (emb, grad) eager %s capture %s replay %s' % (patch, S, errs[0], errs[1], errs[2]))
     for e_emb, e_grad in errs:
