@@ -36,6 +36,10 @@ struct GemmEpi {
   int act = 0;                     // 1 = QuickGELU x*sigmoid(1.702x)
   int unpatch_p = 0;               // >0: out_f32 is [S,3,R,R]; row = s*g*g + gy*g + gx, col = c*p*p + py*p + px
   int unpatch_g = 0;
+  // remainder rows [tail_m0, tail_m) of a one-wave launch (BN = 384): computed by the epilogue warps with mma.sync (gemm_tail_task)
+  const bf16* tail_a = nullptr;    // A [tail_m, K]
+  const bf16* tail_b = nullptr;    // B [N, K]
+  int tail_m0 = 0, tail_m = 0;
 };
 
 struct GemmShape { int M, N, K; };
@@ -249,6 +253,61 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ---- remainder rows of a "one-wave" GEMM ---------------------------------------------------------------------------------
+// The 384-wide pair tiles cover the first floor(M / 256) * 256 rows in exactly one wave; the last M % 256 (<= 64) rows -- 0.3 % of
+// the work at M = 9500 -- are computed by the epilogue warps of the same kernel while they would otherwise wait for the main loop:
+// one warp task = 8 output columns x 16 rows on the legacy tensor path (mma.sync m16n8k16), operands straight from global / L2
+// (no shared memory), 8 k-chunks x 3 x 16 B per lane in flight. K is consumed 32 at a time with ONE 16-byte load per operand row:
+// feeding the A and B fragments through the same k permutation leaves the dot products unchanged.
+__device__ __forceinline__ void mma16816_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int EPI>
+__device__ __noinline__ void gemm_tail_task(int task, int lane, int N, int K, const GemmEpi& epi) {
+  const bf16* __restrict__ A = epi.tail_a; const bf16* __restrict__ B = epi.tail_b;
+  const int M = epi.tail_m, g = lane >> 2, t = lane & 3;
+  const int ncol = N / 8;
+  const int n0 = (task % ncol) * 8, m0 = epi.tail_m0 + (task / ncol) * 16;
+  const int r0 = m0 + g, r1 = r0 + 8;
+  const bf16* bp = B + (size_t)(n0 + g) * K + 8 * t;
+  const bf16* a0p = A + (size_t)min(r0, M - 1) * K + 8 * t;
+  const bf16* a1p = A + (size_t)min(r1, M - 1) * K + 8 * t;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr int U = 8;
+  for (int k0 = 0; k0 < K; k0 += 32 * U) {
+    uint4 bq[U], al[U], ah[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + 32 * u;
+      const bool ok = k < K;
+      bq[u] = ok ? __ldg(reinterpret_cast<const uint4*>(bp + k)) : make_uint4(0u, 0u, 0u, 0u);
+      al[u] = ok ? __ldg(reinterpret_cast<const uint4*>(a0p + k)) : make_uint4(0u, 0u, 0u, 0u);
+      ah[u] = ok ? __ldg(reinterpret_cast<const uint4*>(a1p + k)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      mma16816_bf16(acc, al[u].x, ah[u].x, al[u].y, ah[u].y, bq[u].x, bq[u].y);
+      mma16816_bf16(acc, al[u].z, ah[u].z, al[u].w, ah[u].w, bq[u].z, bq[u].w);
+    }
+  }
+  const int col = n0 + 2 * t;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = h ? r1 : r0;
+    if (r >= M) continue;                       // rows clamped on load are simply not stored
+    const float v0 = acc[2 * h], v1 = acc[2 * h + 1];
+    const size_t off = (size_t)r * N + col;
+    if (EPI == EPI_BIAS_RESID) {
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(epi.bias + col)), rr = __ldg(reinterpret_cast<const float2*>(epi.resid + off));
+      *reinterpret_cast<float2*>(epi.out_f32 + off) = make_float2(v0 + bb.x + rr.x, v1 + bb.y + rr.y);
+    } else if (EPI == EPI_BF16) {
+      *reinterpret_cast<uint32_t*>(epi.out_bf16 + off) = pack_bf16(v0, v1);
+    }
+  }
+}
+
 constexpr int EPI_TILE_BYTES = 32 * 128;      // one ring tile: 32 rows x 128 B
 
 template <int BN, int STAGES, int CG, int NBUF>
@@ -395,6 +454,14 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // groups half, half+2, ... (half = (w-4)/4) of every tile of this CTA.
     const int ew = warp - 4, q = warp & 3, half = ew >> 2;
     const uint32_t ring = smem_u32(smem + L::EPI_OFFSET + ew * (NBUF * EPI_TILE_BYTES));
+    if constexpr (BN == 384 && (EPI == EPI_BF16 || EPI == EPI_BIAS_RESID)) {
+      // remainder rows of a one-wave launch: warp tasks spread over all epilogue warps of the grid, done while the main loop runs
+      if (epi.tail_m > epi.tail_m0) {
+        const int ntasks = (shp.N / 8) * ((epi.tail_m - epi.tail_m0 + 15) / 16);
+        for (int task = (int)blockIdx.x * GEMM_EPI_WARPS + ew; task < ntasks; task += (int)gridDim.x * GEMM_EPI_WARPS)
+          gemm_tail_task<EPI>(task, lane, shp.N, shp.K, epi);
+      }
+    }
     if constexpr (EPI == EPI_UNPATCH) {
       // ---- patch-embed data gradient: the NCHW destination of a 32-row tile is 32 scattered 128-byte segments (one per patch),
       // not a TMA box: 32x32 fp32 chunks are transposed through one ring tile and stored row-contiguously by the lanes.

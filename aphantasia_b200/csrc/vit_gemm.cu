@@ -82,72 +82,6 @@ static std::vector<double> g_prof_flops;
 // Read by the tests to prove which kernel a shape really ran (aph_gemm_variant_launches).
 static std::atomic<long long> g_variant_launches[4][EPI_KINDS];
 
-// ---- remainder rows of a "one-wave" GEMM ---------------------------------------------------------------------------------
-// The 384-wide pair tiles cover the first floor(M / 256) * 256 rows in exactly one wave; the last M % 256 (<= 64) rows -- 0.3 % of
-// the work at M = 9500 -- run here on the legacy tensor path (mma.sync m16n8k16), launched on a side stream so that its one-warp
-// CTAs share the SMs with the persistent kernel (they use no shared memory). K is consumed 32 at a time with ONE 16-byte
-// load per operand row: feeding A and B fragments through the same k permutation leaves the dot products unchanged.
-__device__ __forceinline__ void mma16816_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-template <int EPI>
-__global__ void __launch_bounds__(32) k_gemm_tail(const bf16* __restrict__ A, const bf16* __restrict__ B, int M0, int M, int N, int K, GemmEpi epi) {
-  // one WARP per (8 output columns, 16 remainder rows): no shared memory (the persistent main kernel leaves < 2 KB per SM) and
-  // enough independent warps (N/8 x rows/16) and loads in flight (8 k-chunks x 3 x 16 B per lane) to hide the L2 / HBM latency
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int n0 = blockIdx.x * 8, m0 = M0 + blockIdx.y * 16;
-  const int r0 = m0 + g, r1 = r0 + 8;
-  const bf16* bp = B + (size_t)(n0 + g) * K + 8 * t;
-  const bf16* a0p = A + (size_t)min(r0, M - 1) * K + 8 * t;
-  const bf16* a1p = A + (size_t)min(r1, M - 1) * K + 8 * t;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  constexpr int U = 8;
-  for (int k0 = 0; k0 < K; k0 += 32 * U) {
-    uint4 bq[U], al[U], ah[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int k = k0 + 32 * u;
-      const bool ok = k < K;
-      bq[u] = ok ? __ldg(reinterpret_cast<const uint4*>(bp + k)) : make_uint4(0u, 0u, 0u, 0u);
-      al[u] = ok ? __ldg(reinterpret_cast<const uint4*>(a0p + k)) : make_uint4(0u, 0u, 0u, 0u);
-      ah[u] = ok ? __ldg(reinterpret_cast<const uint4*>(a1p + k)) : make_uint4(0u, 0u, 0u, 0u);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      mma16816_bf16(acc, al[u].x, ah[u].x, al[u].y, ah[u].y, bq[u].x, bq[u].y);
-      mma16816_bf16(acc, al[u].z, ah[u].z, al[u].w, ah[u].w, bq[u].z, bq[u].w);
-    }
-  }
-  const int col = n0 + 2 * t;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int r = h ? r1 : r0;
-    if (r >= M) continue;                       // rows clamped on load are simply not stored
-    const float v0 = acc[2 * h], v1 = acc[2 * h + 1];
-    const size_t off = (size_t)r * N + col;
-    if (EPI == EPI_BIAS_RESID) {
-      const float2 bb = __ldg(reinterpret_cast<const float2*>(epi.bias + col)), rr = __ldg(reinterpret_cast<const float2*>(epi.resid + off));
-      *reinterpret_cast<float2*>(epi.out_f32 + off) = make_float2(v0 + bb.x + rr.x, v1 + bb.y + rr.y);
-    } else {
-      *reinterpret_cast<uint32_t*>(epi.out_bf16 + off) = pack_bf16(v0, v1);
-    }
-  }
-}
-
-// fork / join helpers: the tail kernel runs on a side stream ordered after everything already queued on `st`, and `st` waits for it
-// after the main kernel has been queued (also valid while `st` is being captured into a CUDA graph: the side stream joins the capture)
-static cudaStream_t g_side = nullptr;
-static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
-static int side_prepare() {
-  if (g_side) return 0;
-  APH_CUDA_OK(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
-  APH_CUDA_OK(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
-  APH_CUDA_OK(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
-  return 0;
-}
-
 template <int BN, int EPI, int CG>
 static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st) {
   using E = EpiTraits<EPI>;
@@ -204,27 +138,22 @@ int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi,
   if (pair < 0) { const char* e = getenv("APH_GEMM_2CTA"); pair = (e && e[0] == '0') ? 0 : 1; }
   const bool use_pair = pair && shp.N % 256 == 0 && ((shp.M + 255) / 256) * (shp.N / 256) >= kNumSMs / 2;
   // "one-wave" tiles: N a multiple of 384 and floor(M/256) * N/384 pair tiles that fit the 74 SM pairs at once (the N = 768 GEMMs of
-  // ViT-B at M ~ 9500: 37 x 2 = 74). Two 256-wide waves with the second 54 % full become one; the < 64 remainder rows go to k_gemm_tail.
+  // ViT-B at M ~ 9500: 37 x 2 = 74). Two 256-wide waves with the second 54 % full become one; the <= 64 remainder rows are computed
+  // inside the same kernel by its epilogue warps (idle during the main loop) on the legacy mma.sync path.
+  // MEASURED (profiles/README.md, r2g): not a win -- 165.0 vs 168.1 steps/s at C2. One 384-wide tile per pair has 25 % less main-loop
+  // work than two 256-wide rounds but its epilogue is fully exposed, the N = 128 second instruction re-reads A from shared memory and
+  // only 4 stages fit. Kept as an opt-in experiment (APH_GEMM_ONEWAVE=1); parity-tested either way.
   static int onewave = -1;
-  if (onewave < 0) { const char* e = getenv("APH_GEMM_ONEWAVE"); onewave = (e && e[0] == '0') ? 0 : 1; }
+  if (onewave < 0) { const char* e = getenv("APH_GEMM_ONEWAVE"); onewave = (e && e[0] == '1') ? 1 : 0; }
   if (onewave && pair && (kind == EPI_BF16 || kind == EPI_BIAS_RESID) && shp.N % 384 == 0) {
     const int mt = shp.M / 256, rem = shp.M - mt * 256, tiles = mt * (shp.N / 384);
     if (mt >= 1 && tiles <= kNumSMs / 2 && 2 * tiles > kNumSMs / 2 && rem <= 64) {
+      // the main kernel covers rows [0, mt*256) with TMA-clipped tensor maps; its epilogue warps compute the remainder rows with
+      // mma.sync while the main loop runs (tc_gemm.cuh: gemm_tail_task)
       GemmShape main_shp{mt * 256, shp.N, shp.K};
-      if (rem > 0) {
-        if (int e = side_prepare()) return e;
-        APH_CUDA_OK(cudaEventRecord(g_ev_fork, st));
-        APH_CUDA_OK(cudaStreamWaitEvent(g_side, g_ev_fork, 0));
-        const dim3 tgrid(shp.N / 8, (rem + 15) / 16);
-        if (kind == EPI_BF16) k_gemm_tail<EPI_BF16><<<tgrid, 32, 0, g_side>>>((const bf16*)A, (const bf16*)B, mt * 256, shp.M, shp.N, shp.K, epi);
-        else k_gemm_tail<EPI_BIAS_RESID><<<tgrid, 32, 0, g_side>>>((const bf16*)A, (const bf16*)B, mt * 256, shp.M, shp.N, shp.K, epi);
-        APH_LAUNCH_OK();
-        APH_CUDA_OK(cudaEventRecord(g_ev_join, g_side));
-      }
-      const int rc = (kind == EPI_BF16) ? launch_cfg<384, EPI_BF16, 2>(A, B, main_shp, epi, st) : launch_cfg<384, EPI_BIAS_RESID, 2>(A, B, main_shp, epi, st);
-      if (rc) return rc;
-      if (rem > 0) APH_CUDA_OK(cudaStreamWaitEvent(st, g_ev_join, 0));
-      return 0;
+      GemmEpi e2 = epi;
+      e2.tail_a = reinterpret_cast<const bf16*>(A); e2.tail_b = reinterpret_cast<const bf16*>(B); e2.tail_m0 = mt * 256; e2.tail_m = shp.M;
+      return (kind == EPI_BF16) ? launch_cfg<384, EPI_BF16, 2>(A, B, main_shp, e2, st) : launch_cfg<384, EPI_BIAS_RESID, 2>(A, B, main_shp, e2, st);
     }
   }
 #define APH_GEMM_CASE(K) case K: return use_pair ? launch_cfg<256, K, 2>(A, B, shp, epi, st) : launch_cfg<128, K, 1>(A, B, shp, epi, st);

@@ -21,8 +21,8 @@ from aphantasia_b200 import _lib  # noqa: E402
 lib, ck = _lib.lib(), _lib.check
 M = 9500
 SHAPES = [('bias_bf16', M, 2304, 768, 'qkv'), ('bias_resid', M, 768, 768, 'out_proj + residual'), ('bias_gelu', M, 3072, 768, 'fc1 + QuickGELU'),
-          ('bias_resid', M, 768, 3072, 'fc2 + residual'), ('gelugrad', M, 3072, 768, 'd fc2 x gelu\''), ('f32', M, 768, 3072, 'd fc1'),
-          ('bf16', M, 768, 768, 'd out_proj'), ('f32', M, 768, 2304, 'd qkv')]
+          ('bias_resid', M, 768, 3072, 'fc2 + residual'), ('gelugrad', M, 3072, 768, 'd fc2 x gelu\''), ('bf16', M, 768, 3072, 'd fc1'),
+          ('bf16', M, 768, 768, 'd out_proj'), ('bf16', M, 768, 2304, 'd qkv')]
 PER_STEP = {'qkv': 12, 'out_proj + residual': 12, 'fc1 + QuickGELU': 12, 'fc2 + residual': 12, 'd fc2 x gelu\'': 12, 'd fc1': 12, 'd out_proj': 12, 'd qkv': 12}
 flushbuf = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 

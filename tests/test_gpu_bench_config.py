@@ -6,6 +6,7 @@ small-shape tests of test_gpu_parity.py never reach those code paths. Reference 
 (encode_image at S=190), :240 (slice_imgs), :235-295 (whole step). Tolerances: north_star (1e-3 fp32, 2e-2 bf16), norm-wise.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -109,8 +110,8 @@ def test_pair_gemm_epilogue_kinds_at_bench_size(L, kind, M, N, K):
         checks = [(out, ref, 1e-5)]
     torch.cuda.synchronize()
     assert pair_launches() == before + 1, 'this shape did not run a cta_group::2 pair kernel'
-    if kind in ('bf16', 'bias_resid') and N == 768:
-        assert lib.aph_gemm_variant_launches(3, EPI[kind]) >= 1, 'N = 768 at this M should take the one-wave 256x384 tiles (+ remainder-row kernel)'
+    if kind in ('bf16', 'bias_resid') and N == 768 and os.environ.get('APH_GEMM_ONEWAVE') == '1':
+        assert lib.aph_gemm_variant_launches(3, EPI[kind]) >= 1, 'N = 768 at this M should take the one-wave 256x384 tiles (+ in-kernel remainder rows)'
     for got, want, tol in checks:
         assert torch.isfinite(got).all()
         assert _rel(got, want) < tol, (kind, M, N, K, _rel(got, want))
