@@ -33,7 +33,9 @@ class _SliceImgs(torch.autograd.Function):
         table_dev, = ctx.saved_tensors
         H, W, pad_top, pad_left, S, size, kind, scale = ctx.meta
         g = grad_out.contiguous().float()
-        gc = _tpool.empty((1, 3, H, W))
+        gc = _dist.symm_empty((1, 3, H, W)) if (_dist.world() > 1 and (3 * H * W) % 4 == 0) else None      # symmetric memory: own all-reduce kernel
+        if gc is None:
+            gc = _tpool.empty((1, 3, H, W))
         check(lib().aph_sample_bwd(g.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, gc.data_ptr(),
                                    stream_ptr()), 'aph_sample_bwd')
         if _dist.world() > 1:

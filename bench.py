@@ -114,7 +114,11 @@ class DeviceStep:
         self.crops = torch.empty(S_local, 3, 224, 224, **f32); self.g_crops = torch.empty_like(self.crops)
         self.emb = torch.empty(S_local, 512, **f32); self.g_emb = torch.empty_like(self.emb)
         self.loss = torch.zeros((), **f32)
-        self.g_rgb = torch.empty(3, H, W, **f32); self.g_params = torch.empty_like(self.params)
+        from aphantasia_b200 import _dist
+        self._dist = _dist
+        g_sym = _dist.symm_empty((3, H, W)) if world > 1 else None           # symmetric memory: our own NVLS / peer all-reduce kernel
+        self.g_rgb = g_sym if g_sym is not None else torch.empty(3, H, W, **f32)
+        self.g_params = torch.empty_like(self.params)
         self.m = torch.zeros_like(self.params); self.v = torch.zeros_like(self.params)
         self.t = 0
         self.ev = None
@@ -143,7 +147,7 @@ class DeviceStep:
         self._mark('sample_bwd')
         if self.world > 1:
             self.g_rgb.mul_(float(self.S) / float(self.S_total))
-            torch.distributed.all_reduce(self.g_rgb)
+            self._dist.all_reduce_sum_(self.g_rgb)
             self._mark('allreduce')
         ck(lib.aph_synth_fft_bwd(self.gen.plan, self.g_rgb.data_ptr(), self.rgb.data_ptr(), self.x_raw.data_ptr(), self.stats.data_ptr(),
                                  self.gen.scale.data_ptr(), 1.0, self.colmat, 1, self.g_params.data_ptr(), st), 'synth_bwd')
@@ -318,7 +322,9 @@ def run_ours(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl')
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
-    from aphantasia_b200 import _lib, _rng
+    os.environ['APH_SYNC_SEED'] = '0'
+    from aphantasia_b200 import _dist, _lib, _rng
+    _dist.init()
     lo, hi = _rng.shard_range(S_TOTAL, rank, world)
     if world == 1 and os.environ.get('APH_BENCH_SHARD_OF'):      # profiling knob: one rank's shard of an N-GPU run on a single GPU (no all-reduce)
         lo, hi = _rng.shard_range(S_TOTAL, 0, int(os.environ['APH_BENCH_SHARD_OF']))
@@ -368,9 +374,6 @@ def run_ours(args):
             print(json.dumps({'value': K / t_dev, 'ms_per_step': 1e3 * t_dev / K, 'stages_ms': stages, 'gemm': gemm, 'note': 'device leg only'}))
         return
     # ---- end-to-end leg through the public API (e2e)
-    from aphantasia_b200 import _dist
-    os.environ['APH_SYNC_SEED'] = '0'
-    _dist.init()
     api = ApiStep()
     t_api = timed(api.step, K, Wm, barrier)
     t = torch.tensor([t_api], device='cuda', dtype=torch.float64)
@@ -399,6 +402,9 @@ def run_ours(args):
             finally:
                 shutil.rmtree(d, ignore_errors=True)
 
+    collective = _dist.collective_mode()
+    coll_err = _dist.collective_error() if world > 1 else False
+    assert not coll_err, 'a rank barrier of the symmetric all-reduce timed out'
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -422,7 +428,7 @@ def run_ours(args):
         'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': 1e3 * t_dev / K, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic (seeded spectrum, seeded synthetic ViT-B/32 weights, seeded text embedding)',
         'config': {'workload': WORKLOAD,
-                   'parallelism': 'samples sharded over %d GPU(s), one NCCL all-reduce of dRGB per step' % world if world > 1 else 'single GPU',
+                   'parallelism': ('samples sharded over %d GPU(s), one all-reduce of dRGB per step (%s)' % (world, collective)) if world > 1 else 'single GPU',
                    'l2': 'working set per step (~1.9 GB of saved activations) exceeds the 126 MB L2; no explicit flush'},
         'e2e': {'value': K / t_api, 'unit': 'steps/s', 'h2d_bytes_per_step': (hi - lo) * 24 * 4, 'd2h_bytes_per_step': 4,
                 'ms_per_step': 1e3 * t_api / K, 'path': 'fft_image/to_valid_rgb/slice_imgs/encode_image/sim_func + backward + torch.optim.Adam'},

@@ -210,6 +210,15 @@ int aph_synth_fft_bwd_adam(aph_fft_plan* plan, const float* grad_out, const floa
                            int apply_sigmoid, float* grad_params, float* params, float* m, float* v,
                            float lr, float b1, float b2, float eps, int step, void* stream);
 
+/* ================= multi-GPU exchange ==========================================
+ * In-place all-reduce(SUM) of a fp32 buffer in SYMMETRIC memory (the canvas gradient dRGB [3,H,W], replacing the
+ * single NCCL all-reduce of the path): one kernel, two shots over NVSwitch multicast (multimem.ld_reduce / multimem.st;
+ * mc_ptr = multicast address) or, with mc_ptr == 0, over the peers' mapped pointers. peer_ptrs: HOST array[world] of
+ * every rank's device mapping of the buffer; signal_pads_dev: DEVICE array[world] of pointers to zero-initialised
+ * uint32 signal pads (>= 32*world words each); numel % 4 == 0. err_flag (device int) is set if a barrier timed out.  */
+int aph_allreduce_sym(uint64_t mc_ptr, const uint64_t* peer_ptrs, const uint64_t* signal_pads_dev, int rank, int world,
+                      int64_t numel, int* err_flag, void* stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches)                 */
 int64_t aph_launch_count(void);
 

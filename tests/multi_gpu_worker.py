@@ -46,8 +46,9 @@ def main():
         _dist.all_reduce_sum_(w)
         losses.append(float(w.item()))
     torch.cuda.synchronize()
+    assert not _dist.collective_error(), 'a rank barrier of the symmetric all-reduce timed out'
     if st['rank'] == 0:
-        torch.save({'loss': losses, 'grad': grad0.cpu(), 'params': params[0].detach().cpu(), 'world': st['world'], 'local_crops': int(crops.shape[0])}, out)
+        torch.save({'collective': _dist.collective_mode(), 'loss': losses, 'grad': grad0.cpu(), 'params': params[0].detach().cpu(), 'world': st['world'], 'local_crops': int(crops.shape[0])}, out)
     if st['world'] > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

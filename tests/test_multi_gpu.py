@@ -21,13 +21,14 @@ def _port():
     s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _run(world, out, args):
+def _run(world, out, args, env_add=None):
     if world == 1:
         cmd = [sys.executable, WORKER, out] + args
     else:
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world), '--master-addr', '127.0.0.1',
                '--master-port', str(_port()), WORKER, out] + args
     env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+    env.update(env_add or {})
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     return torch.load(out)
@@ -38,18 +39,21 @@ def _rel(a, b):
 
 
 @pytest.mark.skipif(NGPU < 2, reason='needs at least 2 GPUs')
+@pytest.mark.parametrize('mode', ['sym', 'nccl'])
 @pytest.mark.parametrize('world,H,W,S,patch,sim', [(2, 360, 640, 23, 32, 'mix'), (4, 720, 1280, 87, 16, 'cossim'), (8, 720, 1280, 190, 32, 'mix')])
-def test_n_rank_equals_one_rank(tmp_path, world, H, W, S, patch, sim):
+def test_n_rank_equals_one_rank(tmp_path, world, H, W, S, patch, sim, mode):
+    """mode 'sym': our own NVLS / peer-memory all-reduce kernel over symmetric memory (csrc/comm.cu); 'nccl': dist.all_reduce."""
     if NGPU < world:
         pytest.skip('needs %d GPUs' % world)
     args = [str(H), str(W), str(S), str(patch), sim]
     one = _run(1, str(tmp_path / 'one.pt'), args)
-    many = _run(world, str(tmp_path / 'many.pt'), args)
+    many = _run(world, str(tmp_path / 'many.pt'), args, {'APH_COLLECTIVE': mode})
+    assert many['collective'] == 'nccl' if mode == 'nccl' else many['collective'] in ('nvls', 'p2p', 'nccl')
     assert many['world'] == world and one['world'] == 1
     base, rem = divmod(S, world)
     assert many['local_crops'] == base + (1 if rem > 0 else 0)                       # rank 0 holds the larger shard
     assert abs(many['loss'][0] - one['loss'][0]) < 1e-5 and abs(many['loss'][1] - one['loss'][1]) < 1e-4
     e_g, e_p = _rel(many['grad'], one['grad']), _rel(many['params'], one['params'])
-    print('world %d S=%d: rel err grad %.3e params-after-2-steps %.3e' % (world, S, e_g, e_p))
+    print('world %d S=%d (%s exchange): rel err grad %.3e params-after-2-steps %.3e' % (world, S, many['collective'], e_g, e_p))
     assert e_g < 1e-5
     assert e_p < 5e-3          # Adam with beta1 = 0 moves every element by ~lr*sign(g): elements whose gradient is at round-off level may flip
