@@ -4,7 +4,9 @@ The reference is single-process and never seeds its RNGs. With N ranks every ran
 host random stream (so the crop table is identical and results do not depend on N) and start from the
 same parameters: rank 0 draws one seed, broadcasts it, and every rank seeds torch + numpy with it.
 """
+import atexit
 import os
+import sys
 
 import numpy as np
 import torch
@@ -24,6 +26,7 @@ def init():
             backend = 'nccl' if torch.cuda.is_available() else 'gloo'
             os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
             dist.init_process_group(backend=backend)
+            atexit.register(_shutdown)          # a script that knows nothing about ranks (clip_fft.py) never destroys the group itself
         _state['rank'], _state['world'] = dist.get_rank(), dist.get_world_size()
         if os.environ.get('APH_SYNC_SEED', '1') == '1':
             dev = torch.device('cuda') if backend_is_nccl() else torch.device('cpu')
@@ -32,6 +35,17 @@ def init():
             torch.manual_seed(int(seed.item())); np.random.seed(int(seed.item()) % (2 ** 32))
     _state['init'] = True
     return _state
+
+
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 def backend_is_nccl():
@@ -69,10 +83,6 @@ def symm_empty(shape):
             import ctypes as C
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
-            try:
-                symm.enable_symm_mem_for_group(dist.group.WORLD.group_name)      # needed by older torch; a no-op / deprecated on newer ones
-            except Exception:
-                pass
             ring = []
             for _ in range(2):
                 t = symm.empty(key, dtype=torch.float32, device=torch.device('cuda', torch.cuda.current_device()))
@@ -85,11 +95,11 @@ def symm_empty(shape):
             _sym['mode'] = 'nvls' if ring[0]['mc'] else 'p2p'
             ent = _sym['bufs'][key] = {'ring': ring, 'next': 0}
             if rank() == 0:
-                print(' [aphantasia_b200] gradient exchange: own %s all-reduce kernel over symmetric memory (%d ranks)' % (_sym['mode'], world()))
+                sys.stderr.write(' [aphantasia_b200] gradient exchange: own %s all-reduce kernel over symmetric memory (%d ranks)\n' % (_sym['mode'], world()))
         except Exception as ex:           # symmetric memory / multicast not available on this box: NCCL does the exchange
             _sym['mode'] = 'nccl'
             if rank() == 0:
-                print(' [aphantasia_b200] symmetric memory unavailable (%r): gradient exchange through NCCL all_reduce' % (ex,))
+                sys.stderr.write(' [aphantasia_b200] symmetric memory unavailable (%r): gradient exchange through NCCL all_reduce\n' % (ex,))
             return None
     slot = ent['ring'][ent['next']]
     ent['next'] ^= 1

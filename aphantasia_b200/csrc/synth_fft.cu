@@ -34,6 +34,7 @@ struct FftPlanImpl {
   float2* T = nullptr;     // [3][H][Wh] complex scratch (column-transformed spectrum / its gradient)
   float*  gimg = nullptr;  // [3][H][W] scratch (dL/d img)
   int colC;                // columns per CTA in the column pass
+  bool colSingle = false;  // single-buffer / in-register-stage column kernel (long columns)
   int rowP;                // row pairs per CTA in the row pass
   size_t smem_col, smem_row;
 };
@@ -131,6 +132,80 @@ __device__ float2* fft_lines(float2* a, float2* b, const float2* tw, int N, cons
   return a;
 }
 
+// Single-buffer variant for long columns (H > ~750: 4K canvases). A Stockham stage reads and writes different positions of the
+// SAME buffer, so every thread first pulls ALL inputs of its butterflies into registers, the block synchronises, then the outputs
+// are written: one buffer instead of two lets a CTA hold 8 columns of 2160 complex values (64-byte global segments instead of the
+// 16-byte ones the two-buffer kernel is reduced to at that length). Requires lines * N / R <= (36 / R) * blockDim butterflies per stage.
+template <int R, bool CONJ>
+__device__ __forceinline__ void fft_stage_inreg(float2* __restrict__ buf, const float2* __restrict__ tw, int N, int Ns, int lines, int LS) {
+  constexpr int MAXB = 36 / R;
+  const int nb = N / R, total = lines * nb;
+  const int tstride = N / (Ns * R), rstride = N / R;
+  float2 v[MAXB][R];
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) {
+    const int idx = threadIdx.x + b * blockDim.x;
+    if (idx < total) {
+      const int line = idx / nb, j = idx - line * nb, k = j % Ns;
+      const float2* src = buf + line * LS;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float2 x = src[j + r * nb];
+        if (r > 0) { float2 w = tw[r * k * tstride]; if (CONJ) w.y = -w.y; x = cmul(x, w); }
+        v[b][r] = x;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) {
+    const int idx = threadIdx.x + b * blockDim.x;
+    if (idx < total) {
+      const int line = idx / nb, j = idx - line * nb, k = j % Ns;
+      float2* dst = buf + line * LS + (j - k) * R + k;
+      if (R == 2) {
+        dst[0] = make_float2(v[b][0].x + v[b][1].x, v[b][0].y + v[b][1].y);
+        dst[Ns] = make_float2(v[b][0].x - v[b][1].x, v[b][0].y - v[b][1].y);
+      } else if (R == 4) {
+        const float2 a = make_float2(v[b][0].x + v[b][2].x, v[b][0].y + v[b][2].y), bb = make_float2(v[b][0].x - v[b][2].x, v[b][0].y - v[b][2].y);
+        const float2 c = make_float2(v[b][1].x + v[b][3].x, v[b][1].y + v[b][3].y), d = make_float2(v[b][1].x - v[b][3].x, v[b][1].y - v[b][3].y);
+        const float2 id = CONJ ? make_float2(d.y, -d.x) : make_float2(-d.y, d.x);
+        dst[0] = make_float2(a.x + c.x, a.y + c.y); dst[Ns] = make_float2(bb.x + id.x, bb.y + id.y);
+        dst[2 * Ns] = make_float2(a.x - c.x, a.y - c.y); dst[3 * Ns] = make_float2(bb.x - id.x, bb.y - id.y);
+      } else {
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          float2 acc = v[b][0];
+#pragma unroll
+          for (int r = 1; r < R; ++r) {
+            float2 w = tw[((r * q) % R) * rstride];
+            if (CONJ) w.y = -w.y;
+            const float2 t = cmul(v[b][r], w);
+            acc.x += t.x; acc.y += t.y;
+          }
+          dst[q * Ns] = acc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <bool CONJ>
+__device__ void fft_lines_inreg(float2* buf, const float2* tw, int N, const Radices& rad, int lines, int LS) {
+  int Ns = 1;
+  for (int s = 0; s < rad.n; ++s) {
+    const int R = rad.r[s];
+    switch (R) {
+      case 2: fft_stage_inreg<2, CONJ>(buf, tw, N, Ns, lines, LS); break;
+      case 3: fft_stage_inreg<3, CONJ>(buf, tw, N, Ns, lines, LS); break;
+      case 4: fft_stage_inreg<4, CONJ>(buf, tw, N, Ns, lines, LS); break;
+      default: fft_stage_inreg<5, CONJ>(buf, tw, N, Ns, lines, LS); break;      // the plan only selects this kernel for 2-3-5-smooth H
+    }
+    Ns *= R;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Column pass. FWD: in = params [3][H][Wh] complex (+scale, +shift), out = T. !FWD: in = dT, out = dP*scale.
 // Adam state for the fused update (row f2 of SURVEY 8f): the backward's last pass already holds dP = scale * dZ in registers,
@@ -144,8 +219,8 @@ __device__ __forceinline__ float adam_elem(float& p, float& m, float& v, float g
   return p;
 }
 
-template <bool FWD>
-__global__ void __launch_bounds__(256) k_col_fft(const float2* __restrict__ in, float2* __restrict__ out,
+template <bool FWD, bool SINGLE = false>
+__global__ void __launch_bounds__(SINGLE ? 512 : 256, SINGLE ? 1 : 2) k_col_fft(const float2* __restrict__ in, float2* __restrict__ out,
                                                  const float* __restrict__ scale, const float* __restrict__ shift,
                                                  int shift_mode, const float2* __restrict__ twg, int H, int Wh, int C,
                                                  Radices rad, AdamArgs adam) {
@@ -153,7 +228,7 @@ __global__ void __launch_bounds__(256) k_col_fft(const float2* __restrict__ in, 
   const int LS = H + 1;
   float2* tw = smem;                 // [H]
   float2* bufA = tw + H;             // [C][LS]
-  float2* bufB = bufA + C * LS;
+  float2* bufB = bufA + C * LS;      // (unused by the single-buffer variant)
   const int tiles = (Wh + C - 1) / C;
   const int ch = blockIdx.x / tiles, k2base = (blockIdx.x % tiles) * C;
   const int cols = min(C, Wh - k2base);
@@ -176,7 +251,9 @@ __global__ void __launch_bounds__(256) k_col_fft(const float2* __restrict__ in, 
     bufA[c * LS + k1] = v;
   }
   __syncthreads();
-  float2* res = fft_lines<!FWD>(bufA, bufB, tw, H, rad, C, LS);
+  float2* res = bufA;
+  if (SINGLE) fft_lines_inreg<!FWD>(bufA, tw, H, rad, C, LS);
+  else res = fft_lines<!FWD>(bufA, bufB, tw, H, rad, C, LS);
   for (int idx = threadIdx.x; idx < H * C; idx += blockDim.x) {
     const int n1 = idx / C, c = idx - n1 * C;
     if (c < cols) {
@@ -313,6 +390,16 @@ extern "C" int aph_fft_plan_create(aph_fft_plan** plan_out, int H, int W) {
   while (C > 1 && (size_t)(2 * C * (H + 1) + H) * sizeof(float2) > 100 * 1024) C >>= 1;
   p->colC = C;
   p->smem_col = (size_t)(2 * C * (H + 1) + H) * sizeof(float2);
+  if (C < 8) {            // long columns: the single-buffer kernel keeps 8 columns (or as many as 48 values per thread allow) per CTA
+    int C1 = 8;
+    auto fits = [&](int c) {
+      if ((size_t)(c * (H + 1) + H) * sizeof(float2) > 200 * 1024) return false;
+      for (int i = 0; i < p->rh.n; ++i) { const int r = p->rh.r[i]; if (r > 5 || (long long)c * H / r > (long long)(36 / r) * 512) return false; }
+      return true;
+    };
+    while (C1 > 1 && !fits(C1)) --C1;
+    if (C1 > C) { p->colC = C1; p->colSingle = true; p->smem_col = (size_t)(C1 * (H + 1) + H) * sizeof(float2); }
+  }
   int P = 2;
   while (P > 1 && (size_t)(2 * P * (W + 1) + W) * sizeof(float2) > 100 * 1024) P >>= 1;
   p->rowP = P;
@@ -331,8 +418,13 @@ extern "C" int aph_fft_plan_create(aph_fft_plan** plan_out, int H, int W) {
   APH_CUDA_OK(cudaMemcpy(p->twW, tw.data(), W * sizeof(float2), cudaMemcpyHostToDevice));
   APH_CUDA_OK(cudaMalloc(&p->T, (size_t)3 * H * p->Wh * sizeof(float2)));
   APH_CUDA_OK(cudaMalloc(&p->gimg, (size_t)3 * H * W * sizeof(float)));
-  APH_CUDA_OK(cudaFuncSetAttribute(k_col_fft<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_col));
-  APH_CUDA_OK(cudaFuncSetAttribute(k_col_fft<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_col));
+  if (p->colSingle) {
+    APH_CUDA_OK(cudaFuncSetAttribute(k_col_fft<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_col));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_col_fft<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_col));
+  } else {
+    APH_CUDA_OK(cudaFuncSetAttribute(k_col_fft<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_col));
+    APH_CUDA_OK(cudaFuncSetAttribute(k_col_fft<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_col));
+  }
   APH_CUDA_OK(cudaFuncSetAttribute(k_row_c2r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_row));
   APH_CUDA_OK(cudaFuncSetAttribute(k_row_r2c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_row));
   *plan_out = reinterpret_cast<aph_fft_plan*>(p);
@@ -357,8 +449,10 @@ extern "C" int aph_synth_fft_fwd(aph_fft_plan* plan, const float* params, const 
   const int H = p->H, W = p->W, Wh = p->Wh;
   APH_CUDA_OK(cudaMemsetAsync(stats, 0, 4 * sizeof(double), st));
   const int col_tiles = (Wh + p->colC - 1) / p->colC;
-  k_col_fft<true><<<3 * col_tiles, 256, p->smem_col, st>>>(reinterpret_cast<const float2*>(params), p->T, scale, shift,
-                                                          shift_mode, p->twH, H, Wh, p->colC, p->rh, AdamArgs{});
+  if (p->colSingle) k_col_fft<true, true><<<3 * col_tiles, 512, p->smem_col, st>>>(reinterpret_cast<const float2*>(params), p->T, scale, shift,
+                                                                                    shift_mode, p->twH, H, Wh, p->colC, p->rh, AdamArgs{});
+  else k_col_fft<true><<<3 * col_tiles, 256, p->smem_col, st>>>(reinterpret_cast<const float2*>(params), p->T, scale, shift,
+                                                               shift_mode, p->twH, H, Wh, p->colC, p->rh, AdamArgs{});
   APH_LAUNCH_OK();
   const int groups = ((H + 1) / 2 + p->rowP - 1) / p->rowP;
   const float norm = (float)(1.0 / sqrt((double)H * W));
@@ -389,8 +483,10 @@ static int synth_fft_bwd_impl(aph_fft_plan* plan, const float* grad_out, const f
   k_row_r2c<<<3 * groups, 256, p->smem_row, st>>>(p->gimg, x_raw, stats, p->T, p->twW, H, W, Wh, p->rowP, norm, contrast, p->rw);
   APH_LAUNCH_OK();
   const int col_tiles = (Wh + p->colC - 1) / p->colC;
-  k_col_fft<false><<<3 * col_tiles, 256, p->smem_col, st>>>(p->T, reinterpret_cast<float2*>(grad_params), scale, nullptr, 0,
-                                                           p->twH, H, Wh, p->colC, p->rh, adam);
+  if (p->colSingle) k_col_fft<false, true><<<3 * col_tiles, 512, p->smem_col, st>>>(p->T, reinterpret_cast<float2*>(grad_params), scale, nullptr, 0,
+                                                                                     p->twH, H, Wh, p->colC, p->rh, adam);
+  else k_col_fft<false><<<3 * col_tiles, 256, p->smem_col, st>>>(p->T, reinterpret_cast<float2*>(grad_params), scale, nullptr, 0,
+                                                                p->twH, H, Wh, p->colC, p->rh, adam);
   APH_LAUNCH_OK();
   return 0;
 }

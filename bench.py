@@ -309,8 +309,8 @@ def run_supplementary(args):
     api = ApiStep(cfg=cfg)
     t = timed(api.step, args.steps, args.warmup, lambda: None)
     flops = 2.0 * cfg['S'] * F_VIT[cfg['patch']]
-    print(json.dumps({'config': args.config, 'workload': cfg['note'], 'e2e_steps_per_s': args.steps / t, 'ms_per_step': 1e3 * t / args.steps,
-                      'vit_tflops_of_step': flops / (t / args.steps) / 1e12, 'steps': args.steps, 'warmup': args.warmup}))
+    emit({'config': args.config, 'workload': cfg['note'], 'e2e_steps_per_s': args.steps / t, 'ms_per_step': 1e3 * t / args.steps,
+                      'vit_tflops_of_step': flops / (t / args.steps) / 1e12, 'steps': args.steps, 'warmup': args.warmup})
 
 
 def run_ours(args):
@@ -371,7 +371,7 @@ def run_ours(args):
 
     if os.environ.get('APH_BENCH_LEGS', 'all') == 'device':      # profiling runs (ncu) only need the resident leg
         if rank == 0:
-            print(json.dumps({'value': K / t_dev, 'ms_per_step': 1e3 * t_dev / K, 'stages_ms': stages, 'gemm': gemm, 'note': 'device leg only'}))
+            emit({'value': K / t_dev, 'ms_per_step': 1e3 * t_dev / K, 'stages_ms': stages, 'gemm': gemm, 'note': 'device leg only'})
         return
     # ---- end-to-end leg through the public API (e2e)
     api = ApiStep()
@@ -458,7 +458,7 @@ def run_ours(args):
                 out['gpu_eager_baseline'] = gpu_eager_baseline()
             except Exception as ex:
                 out['gpu_eager_baseline'] = {'value': None, 'unit': 'steps/s', 'what': 'failed: %r' % (ex,)}
-    print(json.dumps(out))
+    emit(out)
 
 
 def time_gemms(ds, S):
@@ -524,10 +524,31 @@ def run_reference(args):
            'config': {'workload': WORKLOAD, 'arm': 'CPU oracle port of the reference path on %d host threads' % cores},
            'extrapolated': extrap,
            'cpu_baseline': cb, 'e2e': {'value': v, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON): anything a library prints while we run (NCCL banners, torch notices) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        if _RESULT_LINE:
+            os.write(1, (_RESULT_LINE[-1] + '\n').encode())
+
+
+_RESULT_LINE = []
+
+
+def emit(obj):
+    _RESULT_LINE.append(json.dumps(obj))
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

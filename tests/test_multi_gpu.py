@@ -52,7 +52,9 @@ def test_n_rank_equals_one_rank(tmp_path, world, H, W, S, patch, sim, mode):
     assert many['world'] == world and one['world'] == 1
     base, rem = divmod(S, world)
     assert many['local_crops'] == base + (1 if rem > 0 else 0)                       # rank 0 holds the larger shard
-    assert abs(many['loss'][0] - one['loss'][0]) < 1e-5 and abs(many['loss'][1] - one['loss'][1]) < 1e-4
+    # step 0 must agree to fp32 round-off; after one Adam step (beta1 = 0: every element moves by ~lr * sign(g)) elements whose gradient
+    # is at round-off level may move the other way, so the second loss is only required to stay close
+    assert abs(many['loss'][0] - one['loss'][0]) < 1e-5 and abs(many['loss'][1] - one['loss'][1]) < 3e-3
     e_g, e_p = _rel(many['grad'], one['grad']), _rel(many['params'], one['params'])
     print('world %d S=%d (%s exchange): rel err grad %.3e params-after-2-steps %.3e' % (world, S, many['collective'], e_g, e_p))
     assert e_g < 1e-5
