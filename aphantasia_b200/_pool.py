@@ -14,9 +14,12 @@ _MAX_PER_KEY = 6
 stats = {'hits': 0, 'misses': 0, 'fallbacks': 0}
 
 
+_USE_COUNT = getattr(torch._C, '_storage_Use_Count', None)      # private torch API; without it the pool degrades to plain torch.empty
+
+
 def _in_use(base):
     # references to the StorageImpl: the base tensor itself + the temporary Python storage wrapper made for this query
-    return torch._C._storage_Use_Count(base.untyped_storage()._cdata) > 2
+    return _USE_COUNT(base.untyped_storage()._cdata) > 2
 
 
 def empty(shape, dtype=torch.float32, device=None):
@@ -25,6 +28,9 @@ def empty(shape, dtype=torch.float32, device=None):
     for s in shape:
         n *= int(s)
     dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if _USE_COUNT is None:
+        stats['fallbacks'] += 1
+        return torch.empty(tuple(shape), dtype=dtype, device='cuda')
     key = (dtype, n, dev)
     lst = _bases.setdefault(key, [])
     for base in lst:
