@@ -136,7 +136,9 @@ int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi,
   // 74 SM pairs; smaller problems keep the finer 128 x 128 single-CTA tiling. APH_GEMM_2CTA=0 forces single-CTA tiles.
   static int pair = -1;
   if (pair < 0) { const char* e = getenv("APH_GEMM_2CTA"); pair = (e && e[0] == '0') ? 0 : 1; }
-  const bool use_pair = pair && shp.N % 256 == 0 && ((shp.M + 255) / 256) * (shp.N / 256) >= kNumSMs / 2;
+  // (threshold: from ~40 pair tiles on, one partial round of 256 x 256 pair tiles beats two rounds of 128 x 128 single-CTA tiles, whose
+  // A + B operand reads per MMA exceed the shared-memory bandwidth: the N = 768 GEMMs of a 95-crop shard (N = 2 ranks) have 57)
+  const bool use_pair = pair && shp.N % 256 == 0 && ((shp.M + 255) / 256) * (shp.N / 256) >= 40;
   // "one-wave" tiles: N a multiple of 384 and floor(M/256) * N/384 pair tiles that fit the 74 SM pairs at once (the N = 768 GEMMs of
   // ViT-B at M ~ 9500: 37 x 2 = 74). Two 256-wide waves with the second 54 % full become one; the <= 64 remainder rows are computed
   // inside the same kernel by its epilogue warps (idle during the main loop) on the legacy mma.sync path.
