@@ -420,7 +420,7 @@ def run_ours(args):
     flops_vit = 2.0 * (hi - lo) * F_VIT[PATCH]
     traffic = None
     try:        # DRAM bytes per launch of the same kernel from the committed ncu capture (cannot be measured outside a profiler)
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1h_gemm_traffic.json')))['traffic_bytes_per_launch']
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r2p_gemm_traffic.json')))['traffic_bytes_per_launch']
     except Exception:
         pass
     out = {
@@ -438,7 +438,7 @@ def run_ours(args):
         'roofline': {'bound': 'tensor', 'kernel': 'k_gemm_bf16_tn (tcgen05): all %d launches of one step, CUDA-event pair around each launch '
                                                   'inside the running step (real fused epilogues)' % gemm_live['launches'],
                      'achieved': gemm_live['tflops'], 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': gemm_live['tflops'] / peak_tf, 'traffic': traffic,
-                     'traffic_source': 'profiles/r1h_gemm_traffic.json (ncu dram__bytes_read+write per launch, 100 launches of one C2 step; algorithmic operand+output bytes per launch = 89 MB, the difference is absorbed by the 126 MB L2 between consecutive kernels)',
+                     'traffic_source': 'profiles/r2p_gemm_traffic.json (ncu --set full: dram__bytes_read+write of the 8 GEMM launches of one transformer layer inside a C2 step, per launch; algorithmic operand+output bytes of the same launches = 87 MB per launch, the difference is absorbed by the 126 MB L2 between consecutive kernels)',
                      'peak_source': peak_src, 'gemm_ms_per_step': gemm_live['ms'],
                      'isolated_plain_epilogue': {'tflops': gemm['tflops'], 'ms_per_step': gemm['ms'], 'per_shape_ms': gemm.get('per_shape_ms')},
                      'vit_step_frac': (flops_vit / (1e-3 * (stages.get('vit_fwd', 0) + stages.get('vit_bwd', 0)) + 1e-12)) / 1e12 / peak_tf},
