@@ -170,7 +170,7 @@ CONFIGS = {
 class ApiStep:
     """The same step through the reference-facing Python entry points (what clip_fft.py's train(i) executes)."""
 
-    def __init__(self, seed=0, cfg=None):
+    def __init__(self, seed=0, cfg=None, fused_adam=False):
         from aphantasia_b200 import transforms
         from aphantasia_b200.clip import CLIP, synthetic_visual_state_dict
         from aphantasia_b200.image import dwt_image, fft_image, to_valid_rgb
@@ -188,7 +188,11 @@ class ApiStep:
         self.model = CLIP('ViT-B/%d' % cfg['patch'], synthetic_visual_state_dict(patch=cfg['patch'], seed=0), True)
         g = torch.Generator().manual_seed(1234)
         txt = torch.randn(1, 512, generator=g); self.txt = (10. * txt / txt.norm()).cuda()
-        self.opt = torch.optim.Adam(self.params, 0.05, betas=(.0, .999))
+        if fused_adam:       # what APH_FUSED_ADAM=1 gives the unmodified script: Adam fused into the synthesis backward (row f2)
+            from aphantasia_b200 import optim
+            self.opt = optim.Adam(self.params, 0.05, betas=(.0, .999))
+        else:
+            self.opt = torch.optim.Adam(self.params, 0.05, betas=(.0, .999))
 
     def step(self, i):
         img_out = self.image_f(None)
@@ -380,6 +384,19 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_api = float(t.item())
+    e2e_fused = None
+    if world == 1 and not CONFIGS['c2']['dwt']:
+        del api
+        torch.cuda.empty_cache()
+        api_f = ApiStep(fused_adam=True)
+        t_f = timed(api_f.step, K, Wm, barrier)
+        e2e_fused = {'value': K / t_f, 'unit': 'steps/s', 'ms_per_step': 1e3 * t_f / K,
+                     'what': 'same as e2e with aphantasia_b200.optim.Adam (APH_FUSED_ADAM=1 for the unmodified script): the update runs inside the synthesis backward'}
+        del api_f
+        torch.cuda.empty_cache()
+        api = ApiStep()
+        for i in range(3):
+            api.step(i)
     # the same loop exactly as the unmodified script runs it (empty_cache per step, preview every opt_step), wall-clock incl. the
     # asynchronous JPEG encoder's drain: what a user of clip_fft.py sees at the default --opt_step 1 and at --opt_step 50
     script = {}
@@ -432,6 +449,7 @@ def run_ours(args):
                    'l2': 'working set per step (~1.9 GB of saved activations) exceeds the 126 MB L2; no explicit flush'},
         'e2e': {'value': K / t_api, 'unit': 'steps/s', 'h2d_bytes_per_step': (hi - lo) * 24 * 4, 'd2h_bytes_per_step': 4,
                 'ms_per_step': 1e3 * t_api / K, 'path': 'fft_image/to_valid_rgb/slice_imgs/encode_image/sim_func + backward + torch.optim.Adam'},
+        'e2e_fused_adam': e2e_fused,
         'e2e_script': script or None,
         'gpu_launches': int(launches),
         'clocks': clk,
