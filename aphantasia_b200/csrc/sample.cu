@@ -384,14 +384,15 @@ k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int 
 // Default backward: fp32 shared accumulation (compare-and-swap loops in SASS).
 __global__ void __launch_bounds__(1024, 1)
 k_sample_bwd_cas(const float* __restrict__ grad_out, int H, int W, int pad_top, int pad_left, const float* __restrict__ table,
-             int size, int kind, float* __restrict__ grad_canvas) {
+             int size, int kind, float* __restrict__ grad_canvas, float gscale) {
   extern __shared__ float gA[];
   const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
   const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
   const int n = size * size;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float* go = grad_out + ((size_t)crop * 3 + ch) * n;
-  const float inv_sd = (kind != APH_TF_NONE) ? 1.f / c_std[ch] : 1.f;
+  // gscale: weight of this rank's shard in the all-reduced gradient (S_local / S under torchrun, 1 otherwise), folded in here
+  const float inv_sd = ((kind != APH_TF_NONE) ? 1.f / c_std[ch] : 1.f) * gscale;
   const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
   const TapTables tt = build_taps(gA + ((n + 3) & ~3), p, size, H, W, pad_top, pad_left, scale);
   float* strip = gA + ((n + 3) & ~3) + 16 * size + warp * STRIP;
@@ -590,11 +591,30 @@ extern "C" int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, in
   return 0;
 }
 
+namespace aph {
+__global__ void __launch_bounds__(256) k_scale_inplace(float* __restrict__ p, size_t n, float a) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] *= a;
+}
+}  // namespace aph
+
 static float* g_gA = nullptr;          // stage-1 scratch [S,3,size,size] (library-owned: survives torch.cuda.empty_cache())
 static size_t g_gA_bytes = 0;
 
+static int sample_bwd_impl(const float* grad_out, int H, int W, int pad_top, int pad_left, const float* table, int S,
+                           int size, int kind, float* grad_canvas, float gscale, void* stream);
+
 extern "C" int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, int pad_left, const float* table, int S,
                               int size, int kind, float* grad_canvas, void* stream) {
+  return sample_bwd_impl(grad_out, H, W, pad_top, pad_left, table, S, size, kind, grad_canvas, 1.f, stream);
+}
+
+extern "C" int aph_sample_bwd_scaled(const float* grad_out, int H, int W, int pad_top, int pad_left, const float* table, int S,
+                                     int size, int kind, float gscale, float* grad_canvas, void* stream) {
+  return sample_bwd_impl(grad_out, H, W, pad_top, pad_left, table, S, size, kind, grad_canvas, gscale, stream);
+}
+
+static int sample_bwd_impl(const float* grad_out, int H, int W, int pad_top, int pad_left, const float* table, int S,
+                           int size, int kind, float* grad_canvas, float gscale, void* stream) {
   if (int e = check_sample_args("aph_sample_bwd", H, W, S, size, kind)) return e;
   APH_REQUIRE(grad_canvas, "aph_sample_bwd: null grad_canvas");
   // Measured on B200 (profiles/r1e): the atomic scatter (0.99 ms @ C2) beats this gather (1.85 ms: per-(tile, crop) list
@@ -631,7 +651,7 @@ extern "C" int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, 
       for (int c = 0; c < 3; ++c) pre[c] = 1.f / sd[c];
     }
     dim3 grid(((W + GT_W - 1) / GT_W) * ((H + GT_H - 1) / GT_H), 3);
-    k_sample_bwd_gather<<<grid, 256, 0, st>>>(gsrc, pre[0], pre[1], pre[2], table, S, size, H, W, grad_canvas);
+    k_sample_bwd_gather<<<grid, 256, 0, st>>>(gsrc, pre[0] * gscale, pre[1] * gscale, pre[2] * gscale, table, S, size, H, W, grad_canvas);
     APH_LAUNCH_OK();
     return 0;
   }
@@ -649,8 +669,13 @@ extern "C" int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, 
   // fp32 compare-and-swap kernel (0.581 vs 0.578 ms at C2, profiles/README.md), so the plain fp32 kernel stays the default.
   static int fixed = -1;
   if (fixed < 0) { const char* e = getenv("APH_SAMPLE_BWD_FIXED"); fixed = (e && e[0] == '1') ? 1 : 0; }
-  if (fixed) k_sample_bwd<<<S * 3, 1024, smem, (cudaStream_t)stream>>>(grad_out, H, W, pad_top, pad_left, table, size, kind, grad_canvas);
-  else k_sample_bwd_cas<<<S * 3, 1024, smem, (cudaStream_t)stream>>>(grad_out, H, W, pad_top, pad_left, table, size, kind, grad_canvas);
+  if (fixed) {
+    k_sample_bwd<<<S * 3, 1024, smem, (cudaStream_t)stream>>>(grad_out, H, W, pad_top, pad_left, table, size, kind, grad_canvas);
+    APH_LAUNCH_OK();
+    if (gscale != 1.f) { k_scale_inplace<<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(grad_canvas, (size_t)3 * H * W, gscale); APH_LAUNCH_OK(); }
+    return 0;
+  }
+  k_sample_bwd_cas<<<S * 3, 1024, smem, (cudaStream_t)stream>>>(grad_out, H, W, pad_top, pad_left, table, size, kind, grad_canvas, gscale);
   APH_LAUNCH_OK();
   return 0;
 }

@@ -36,11 +36,11 @@ class _SliceImgs(torch.autograd.Function):
         gc = _dist.symm_empty((1, 3, H, W)) if (_dist.world() > 1 and (3 * H * W) % 4 == 0) else None      # symmetric memory: own all-reduce kernel
         if gc is None:
             gc = _tpool.empty((1, 3, H, W))
-        check(lib().aph_sample_bwd(g.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, gc.data_ptr(),
-                                   stream_ptr()), 'aph_sample_bwd')
+        # each rank's loss is a mean over its own shard: its canvas gradient enters the sum over ranks with weight S_local / S_total
+        # (`scale`, folded into the scatter kernel)
+        check(lib().aph_sample_bwd_scaled(g.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, float(scale), gc.data_ptr(),
+                                          stream_ptr()), 'aph_sample_bwd_scaled')
         if _dist.world() > 1:
-            # each rank's loss is a mean over its own shard: weight by S_local/S_total, then sum over ranks
-            gc.mul_(scale)
             _dist.all_reduce_sum_(gc)
         return gc, None, None
 

@@ -143,10 +143,10 @@ class DeviceStep:
         self._mark('loss')
         ck(lib.aph_vit_bwd(self.vis.handle, self.g_emb.data_ptr(), self.S, self.g_crops.data_ptr(), st), 'vit_bwd')
         self._mark('vit_bwd')
-        ck(lib.aph_sample_bwd(self.g_crops.data_ptr(), H, W, 0, 0, tab.data_ptr(), self.S, 224, 2, self.g_rgb.data_ptr(), st), 'sample_bwd')
+        ck(lib.aph_sample_bwd_scaled(self.g_crops.data_ptr(), H, W, 0, 0, tab.data_ptr(), self.S, 224, 2, float(self.S) / float(self.S_total),
+                                     self.g_rgb.data_ptr(), st), 'sample_bwd')
         self._mark('sample_bwd')
         if self.world > 1:
-            self.g_rgb.mul_(float(self.S) / float(self.S_total))
             self._dist.all_reduce_sum_(self.g_rgb)
             self._mark('allreduce')
         ck(lib.aph_synth_fft_bwd(self.gen.plan, self.g_rgb.data_ptr(), self.rgb.data_ptr(), self.x_raw.data_ptr(), self.stats.data_ptr(),

@@ -119,6 +119,11 @@ int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, int pad_left,
 int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, int pad_left,
                    const float* table, int S, int size, int kind, float* grad_canvas, void* stream);
 
+/* Same with every contribution multiplied by gscale (the weight S_local / S of this rank's shard in the all-reduced
+ * gradient under torchrun: folded into the scatter instead of a separate pass over the canvas).     */
+int aph_sample_bwd_scaled(const float* grad_out, int H, int W, int pad_top, int pad_left,
+                          const float* table, int S, int size, int kind, float gscale, float* grad_canvas, void* stream);
+
 /* HOST function (no GPU work): exact native replay of the reference's per-crop random draws (utils.py:244-247,
  * torchvision RandomPerspective/RandomErasing.get_params, transforms.py:75) continuing torch's CPU generator
  * (torch_state = the torch.get_rng_state() blob, updated in place) and NumPy's legacy MT19937 (np_key[624], *np_pos,
