@@ -220,6 +220,129 @@ k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pa
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Forward, two-kernel form (round 2). The one-kernel form above keeps the resized crop of ONE channel in 196 KB of shared memory and
+// recomputes the rotate / perspective geometry per channel; it is instruction-issue bound (~295 thread instructions per pixel and
+// channel). Here
+//   k_resize : stage 1 alone, SEPARABLE -- a warp owns an output row: vertical 4-tap pass over the crop's columns (coalesced row
+//              reads) into a per-warp strip, then the horizontal 4-tap pass out of the strip; 8 rows of state per CTA, 7 CTAs / SM.
+//              Result A [S,3,size,size] goes to a library scratch buffer (L2 / HBM), or straight to the output for transform kinds
+//              without a warp stage.
+//   k_compose: stages 2-5 for ALL THREE channels of a pixel per thread: one evaluation of the rotate (and perspective) taps,
+//              4 (16) gathers per channel from the scratch image through L1.
+template <bool WRAP>
+__global__ void __launch_bounds__(256)
+k_resize(const float* __restrict__ canvas, int H, int W, int pad_top, int pad_left, const float* __restrict__ table, int size, int rows_per_cta,
+         int cap, int kind, float* __restrict__ dst) {
+  extern __shared__ float rs[];
+  int* xi = reinterpret_cast<int*>(rs);              // [4*size] crop-relative source columns of every output column
+  float* xw = rs + 4 * size;                         // [4*size] their weights
+  const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
+  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  const float* cch = canvas + (size_t)ch * H * W;
+  const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < size; k += blockDim.x) {
+    int idx[4]; float w[4];
+    cubic_taps(k, scale, p.cs, idx, w);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { xi[4 * k + a] = idx[a]; xw[4 * k + a] = w[a]; }
+  }
+  __syncthreads();
+  float* strip = rs + 8 * size + warp * cap;
+  const int n = size * size;
+  float* o = dst + ((size_t)crop * 3 + ch) * n;
+  const float na = (kind == APH_TF_NORMALIZE) ? 1.f / c_std[ch] : 1.f, nb = (kind == APH_TF_NORMALIZE) ? -c_mean[ch] / c_std[ch] : 0.f;
+  const int r_end = min(size, ((int)blockIdx.y + 1) * rows_per_cta);
+  for (int i = blockIdx.y * rows_per_cta + warp; i < r_end; i += 8) {
+    int yidx[4]; float wy[4];
+    cubic_taps(i, scale, p.cs, yidx, wy);
+    const float* rp[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int y = p.oy + yidx[a] - pad_top;
+      if (WRAP) { y %= H; if (y < 0) y += H; }
+      rp[a] = cch + (size_t)y * W;
+    }
+    for (int x = lane; x < p.cs; x += 32) {
+      int col = p.ox + x - pad_left;
+      if (WRAP) { col %= W; if (col < 0) col += W; }
+      float v = wy[0] * __ldg(rp[0] + col);
+      v += wy[1] * __ldg(rp[1] + col); v += wy[2] * __ldg(rp[2] + col); v += wy[3] * __ldg(rp[3] + col);
+      strip[x] = v;
+    }
+    __syncwarp();
+    for (int j = lane; j < size; j += 32) {
+      const int4 xo = *reinterpret_cast<const int4*>(xi + 4 * j);
+      const float4 wx = *reinterpret_cast<const float4*>(xw + 4 * j);
+      float acc = wx.x * strip[xo.x];
+      acc += wx.y * strip[xo.y]; acc += wx.z * strip[xo.z]; acc += wx.w * strip[xo.w];
+      o[i * size + j] = (kind == APH_TF_FAST) ? acc : fmaf(acc, na, nb);
+    }
+    __syncwarp();
+  }
+}
+
+// value of the post-perspective, post-erase image B at integer pixel (y, x) for the three channels
+template <bool PERSP, bool ERASE>
+__device__ __forceinline__ void stageB3(const float* __restrict__ A, int n, const CropParams& p, int y, int x, int size, float w, float (&acc)[3]) {
+  if (ERASE && erased(p, y, x)) return;
+  if (PERSP) {
+    const Bilin b = persp_taps(p, y, x, size);
+    const float mw = (b.w00 + b.w01 + b.w10 + b.w11) * w;
+    const int o = b.y0 * size + b.x0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* Ac = A + (size_t)c * n;
+      float v = 0.f;
+      if (b.w00 != 0.f) v += b.w00 * __ldg(Ac + o);
+      if (b.w01 != 0.f) v += b.w01 * __ldg(Ac + o + 1);
+      if (b.w10 != 0.f) v += b.w10 * __ldg(Ac + o + size);
+      if (b.w11 != 0.f) v += b.w11 * __ldg(Ac + o + size + 1);
+      acc[c] += v * mw;
+    }
+  } else {
+    const int o = y * size + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += w * __ldg(A + (size_t)c * n + o);
+  }
+}
+
+template <bool PERSP, bool ERASE>
+__device__ __forceinline__ void compose3(const float* __restrict__ A, int n, const CropParams& p, int i, int j, int size, float* __restrict__ o) {
+  const Bilin b = rot_taps(p, i, j, size);
+  const float mask = b.w00 + b.w01 + b.w10 + b.w11;
+  float acc[3] = {0.f, 0.f, 0.f};
+  if (b.w00 != 0.f) stageB3<PERSP, ERASE>(A, n, p, b.y0, b.x0, size, b.w00, acc);
+  if (b.w01 != 0.f) stageB3<PERSP, ERASE>(A, n, p, b.y0, b.x0 + 1, size, b.w01, acc);
+  if (b.w10 != 0.f) stageB3<PERSP, ERASE>(A, n, p, b.y0 + 1, b.x0, size, b.w10, acc);
+  if (b.w11 != 0.f) stageB3<PERSP, ERASE>(A, n, p, b.y0 + 1, b.x0 + 1, size, b.w11, acc);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { const float inv_sd = 1.f / c_std[c]; o[(size_t)c * n + i * size + j] = fmaf(acc[c] * mask, inv_sd, -c_mean[c] * inv_sd); }
+}
+
+__global__ void __launch_bounds__(256)
+k_compose(const float* __restrict__ Ag, const float* __restrict__ table, int size, float* __restrict__ out) {
+  const int crop = blockIdx.y, tiles_x = (size + 15) >> 4;
+  const int ti = blockIdx.x / tiles_x, tj = blockIdx.x - ti * tiles_x;
+  const int i = ti * 16 + (threadIdx.x >> 4), j = tj * 16 + (threadIdx.x & 15);
+  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  if (i >= size || j >= size) return;
+  const int n = size * size;
+  const float* A = Ag + (size_t)crop * 3 * n;
+  float* o = out + (size_t)crop * 3 * n;
+  const bool er = (p.flags & APH_FLAG_ERASE) != 0;
+  if (p.flags & APH_FLAG_PERSP) { if (er) compose3<true, true>(A, n, p, i, j, size, o); else compose3<true, false>(A, n, p, i, j, size, o); }
+  else if (identity_rot(p)) {
+    const bool e = erased(p, i, j);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const float inv_sd = 1.f / c_std[c], shift = -c_mean[c] * inv_sd; o[(size_t)c * n + i * size + j] = e ? shift : fmaf(__ldg(A + (size_t)c * n + i * size + j), inv_sd, shift); }
+  }
+  else if (er) compose3<false, true>(A, n, p, i, j, size, o);
+  else compose3<false, false>(A, n, p, i, j, size, o);
+}
+
 // Shared-memory accumulation cell. fp32 atomicAdd on shared memory is a compare-and-swap loop on this architecture
 // (SASS: ATOMS.CAST.SPIN, ~6 instructions and two dependent shared round trips per add; ncu: 31 % of the backward kernel's
 // instructions, 44 % of its stall samples). The opt-in FIXED form (k_sample_bwd, APH_SAMPLE_BWD_FIXED=1) accumulates round(v * scale) with the native integer ATOMS.ADD instead; the
@@ -575,11 +698,54 @@ static int check_sample_args(const char* who, int H, int W, int S, int size, int
   return 0;
 }
 
+static float* g_A = nullptr;           // resized crops [S,3,size,size] between k_resize and k_compose (library-owned scratch)
+static size_t g_A_bytes = 0;
+
 extern "C" int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, int pad_left, const float* table, int S,
                               int size, int kind, float* out, void* stream) {
   if (int e = check_sample_args("aph_sample_fwd", H, W, S, size, kind)) return e;
   if (S == 0) return 0;
   APH_REQUIRE(canvas && table && out, "aph_sample_fwd: null pointer");
+  {
+    // default: the two-kernel form (k_resize + k_compose); APH_SAMPLE_FWD_OLD=1 keeps the one-kernel form (also used when the crop
+    // strips would not fit: canvases beyond ~6000 px on the short side)
+    static int old_path = -1;
+    if (old_path < 0) { const char* e = getenv("APH_SAMPLE_FWD_OLD"); old_path = (e && e[0] == '1') ? 1 : 0; }
+    const int cap = ((H + 2 * pad_top < W + 2 * pad_left ? H + 2 * pad_top : W + 2 * pad_left) + 1 + 3) & ~3;     // crops never exceed the short side of the frame
+    const size_t smem2 = ((size_t)8 * size + (size_t)8 * cap) * sizeof(float);
+    if (!old_path && smem2 <= 200 * 1024) {
+      cudaStream_t st = (cudaStream_t)stream;
+      float* dst = out;
+      if (kind == APH_TF_FAST) {
+        const size_t need = (size_t)S * 3 * size * size * sizeof(float);
+        if (need > g_A_bytes) {
+          APH_CUDA_OK(cudaStreamSynchronize(st));
+          if (g_A) cudaFree(g_A);
+          g_A = nullptr; g_A_bytes = 0;
+          APH_CUDA_OK(cudaMalloc(&g_A, need));
+          g_A_bytes = need;
+        }
+        dst = g_A;
+      }
+      static size_t conf = 0;
+      if (smem2 > conf) {
+        APH_CUDA_OK(cudaFuncSetAttribute(k_resize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        APH_CUDA_OK(cudaFuncSetAttribute(k_resize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        conf = smem2;
+      }
+      const int rows_per_cta = 32;
+      const dim3 g1(S * 3, (size + rows_per_cta - 1) / rows_per_cta);
+      if (pad_top || pad_left) k_resize<true><<<g1, 256, smem2, st>>>(canvas, H, W, pad_top, pad_left, table, size, rows_per_cta, cap, kind, dst);
+      else k_resize<false><<<g1, 256, smem2, st>>>(canvas, H, W, pad_top, pad_left, table, size, rows_per_cta, cap, kind, dst);
+      APH_LAUNCH_OK();
+      if (kind == APH_TF_FAST) {
+        const int tiles = ((size + 15) / 16) * ((size + 15) / 16);
+        k_compose<<<dim3(tiles, S), 256, 0, st>>>(g_A, table, size, out);
+        APH_LAUNCH_OK();
+      }
+      return 0;
+    }
+  }
   const size_t smem = ((size_t)size * size + 4 + 16 * (size_t)size) * sizeof(float);   // no strips in the forward: the rest stays L1
   static size_t configured = 0;
   if (smem > configured) {
