@@ -119,6 +119,9 @@ __device__ __forceinline__ float stageB(const float* __restrict__ A, const CropP
   return A[y * size + x];
 }
 
+__constant__ float c_inv_std[3] = {1.f / 0.26862954f, 1.f / 0.26130258f, 1.f / 0.27577711f};
+__constant__ float c_shift[3] = {-0.48145466f / 0.26862954f, -0.4578275f / 0.26130258f, -0.40821073f / 0.27577711f};
+
 // the rotate stage is the identity resampling (angle 0: theta = [[1, 0], [0, 1]])
 __device__ __forceinline__ bool identity_rot(const CropParams& p) { return p.r00 == 1.f && p.r01 == 0.f && p.r10 == 0.f && p.r11 == 1.f; }
 
@@ -239,7 +242,10 @@ k_resize(const float* __restrict__ canvas, int H, int W, int pad_top, int pad_le
   int* xi = reinterpret_cast<int*>(rs);              // [4*size] crop-relative source columns of every output column
   float* xw = rs + 4 * size;                         // [4*size] their weights
   const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
-  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  __shared__ int s_oy, s_ox, s_cs;
+  if (threadIdx.x == 0) { const float* row = table + (size_t)crop * APH_CROP_PARAM_FLOATS; s_oy = (int)row[APH_F_OFFY]; s_ox = (int)row[APH_F_OFFX]; s_cs = (int)row[APH_F_CSIZE]; }
+  __syncthreads();
+  CropParams p; p.oy = s_oy; p.ox = s_ox; p.cs = s_cs;
   const float* cch = canvas + (size_t)ch * H * W;
   const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -263,14 +269,22 @@ k_resize(const float* __restrict__ canvas, int H, int W, int pad_top, int pad_le
     for (int a = 0; a < 4; ++a) {
       int y = p.oy + yidx[a] - pad_top;
       if (WRAP) { y %= H; if (y < 0) y += H; }
-      rp[a] = cch + (size_t)y * W;
+      rp[a] = cch + y * W + (WRAP ? 0 : p.ox - pad_left);
     }
-    for (int x = lane; x < p.cs; x += 32) {
-      int col = p.ox + x - pad_left;
-      if (WRAP) { col %= W; if (col < 0) col += W; }
-      float v = wy[0] * __ldg(rp[0] + col);
-      v += wy[1] * __ldg(rp[1] + col); v += wy[2] * __ldg(rp[2] + col); v += wy[3] * __ldg(rp[3] + col);
-      strip[x] = v;
+    if (WRAP) {
+      for (int x = lane; x < p.cs; x += 32) {
+        int col = (p.ox + x - pad_left) % W; if (col < 0) col += W;
+        float v = wy[0] * __ldg(rp[0] + col);
+        v += wy[1] * __ldg(rp[1] + col); v += wy[2] * __ldg(rp[2] + col); v += wy[3] * __ldg(rp[3] + col);
+        strip[x] = v;
+      }
+    } else {
+#pragma unroll 4
+      for (int x = lane; x < p.cs; x += 32) {
+        float v = wy[0] * __ldg(rp[0] + x);
+        v += wy[1] * __ldg(rp[1] + x); v += wy[2] * __ldg(rp[2] + x); v += wy[3] * __ldg(rp[3] + x);
+        strip[x] = v;
+      }
     }
     __syncwarp();
     for (int j = lane; j < size; j += 32) {
@@ -294,7 +308,7 @@ __device__ __forceinline__ void stageB3(const float* __restrict__ A, int n, cons
     const int o = b.y0 * size + b.x0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float* Ac = A + (size_t)c * n;
+      const float* Ac = A + c * n;
       float v = 0.f;
       if (b.w00 != 0.f) v += b.w00 * __ldg(Ac + o);
       if (b.w01 != 0.f) v += b.w01 * __ldg(Ac + o + 1);
@@ -305,7 +319,7 @@ __device__ __forceinline__ void stageB3(const float* __restrict__ A, int n, cons
   } else {
     const int o = y * size + x;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) acc[c] += w * __ldg(A + (size_t)c * n + o);
+    for (int c = 0; c < 3; ++c) acc[c] += w * __ldg(A + c * n + o);
   }
 }
 
@@ -318,8 +332,9 @@ __device__ __forceinline__ void compose3(const float* __restrict__ A, int n, con
   if (b.w01 != 0.f) stageB3<PERSP, ERASE>(A, n, p, b.y0, b.x0 + 1, size, b.w01, acc);
   if (b.w10 != 0.f) stageB3<PERSP, ERASE>(A, n, p, b.y0 + 1, b.x0, size, b.w10, acc);
   if (b.w11 != 0.f) stageB3<PERSP, ERASE>(A, n, p, b.y0 + 1, b.x0 + 1, size, b.w11, acc);
+  const int pix = i * size + j;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) { const float inv_sd = 1.f / c_std[c]; o[(size_t)c * n + i * size + j] = fmaf(acc[c] * mask, inv_sd, -c_mean[c] * inv_sd); }
+  for (int c = 0; c < 3; ++c) o[c * n + pix] = fmaf(acc[c] * mask, c_inv_std[c], c_shift[c]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -327,7 +342,10 @@ k_compose(const float* __restrict__ Ag, const float* __restrict__ table, int siz
   const int crop = blockIdx.y, tiles_x = (size + 15) >> 4;
   const int ti = blockIdx.x / tiles_x, tj = blockIdx.x - ti * tiles_x;
   const int i = ti * 16 + (threadIdx.x >> 4), j = tj * 16 + (threadIdx.x & 15);
-  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  __shared__ CropParams sp;                      // the crop's parameters are decoded once per CTA
+  if (threadIdx.x == 0) sp = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  __syncthreads();
+  const CropParams p = sp;
   if (i >= size || j >= size) return;
   const int n = size * size;
   const float* A = Ag + (size_t)crop * 3 * n;
@@ -336,8 +354,9 @@ k_compose(const float* __restrict__ Ag, const float* __restrict__ table, int siz
   if (p.flags & APH_FLAG_PERSP) { if (er) compose3<true, true>(A, n, p, i, j, size, o); else compose3<true, false>(A, n, p, i, j, size, o); }
   else if (identity_rot(p)) {
     const bool e = erased(p, i, j);
+    const int pix = i * size + j;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { const float inv_sd = 1.f / c_std[c], shift = -c_mean[c] * inv_sd; o[(size_t)c * n + i * size + j] = e ? shift : fmaf(__ldg(A + (size_t)c * n + i * size + j), inv_sd, shift); }
+    for (int c = 0; c < 3; ++c) o[c * n + pix] = e ? c_shift[c] : fmaf(__ldg(A + c * n + pix), c_inv_std[c], c_shift[c]);
   }
   else if (er) compose3<false, true>(A, n, p, i, j, size, o);
   else compose3<false, false>(A, n, p, i, j, size, o);
