@@ -31,7 +31,17 @@ struct CropParams {
   float pc[8];
   int ei, ej, eh, ew;
   float r00, r01, r10, r11;
+  float rs[4];     // r.. / (size/2): the affine grid of the rotate stage in normalised coordinates (prescale())
+  float ps[6];     // pc[0..5] / (size/2)
 };
+
+// divisions of the grid builders, hoisted out of the per-pixel code (one CTA = one crop)
+__device__ __forceinline__ void prescale(CropParams& p, int size) {
+  const float half = 0.5f * (float)size;
+  p.rs[0] = p.r00 / half; p.rs[1] = p.r01 / half; p.rs[2] = p.r10 / half; p.rs[3] = p.r11 / half;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) p.ps[i] = p.pc[i] / half;
+}
 
 __device__ __forceinline__ CropParams load_params(const float* __restrict__ row) {
   CropParams p;
@@ -41,6 +51,9 @@ __device__ __forceinline__ CropParams load_params(const float* __restrict__ row)
   p.ei = (int)row[APH_F_ER_I]; p.ej = (int)row[APH_F_ER_J]; p.eh = (int)row[APH_F_ER_H]; p.ew = (int)row[APH_F_ER_W];
   p.r00 = row[APH_F_ROT]; p.r01 = row[APH_F_ROT + 1]; p.r10 = row[APH_F_ROT + 2]; p.r11 = row[APH_F_ROT + 3];
   if (!(p.flags & APH_FLAG_ERASE)) { p.eh = 0; p.ew = 0; }
+  p.rs[0] = p.rs[1] = p.rs[2] = p.rs[3] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) p.ps[i] = 0.f;
   return p;
 }
 
@@ -78,16 +91,15 @@ __device__ __forceinline__ Bilin bilin_taps(float gx, float gy, int size) {
 __device__ __forceinline__ Bilin rot_taps(const CropParams& p, int i, int j, int size) {
   const float half = 0.5f * (float)size;
   const float bx = (float)j + 0.5f - half, by = (float)i + 0.5f - half;
-  const float gx = bx * (p.r00 / half) + by * (p.r01 / half);
-  const float gy = bx * (p.r10 / half) + by * (p.r11 / half);
+  const float gx = bx * p.rs[0] + by * p.rs[1];
+  const float gy = bx * p.rs[2] + by * p.rs[3];
   return bilin_taps(gx, gy, size);
 }
 
 __device__ __forceinline__ Bilin persp_taps(const CropParams& p, int y, int x, int size) {
-  const float half = 0.5f * (float)size;
   const float bx = (float)x + 0.5f, by = (float)y + 0.5f;
-  const float n1x = bx * (p.pc[0] / half) + by * (p.pc[1] / half) + (p.pc[2] / half);
-  const float n1y = bx * (p.pc[3] / half) + by * (p.pc[4] / half) + (p.pc[5] / half);
+  const float n1x = bx * p.ps[0] + by * p.ps[1] + p.ps[2];
+  const float n1y = bx * p.ps[3] + by * p.ps[4] + p.ps[5];
   const float den = bx * p.pc[6] + by * p.pc[7] + 1.f;
   const float inv = __fdividef(1.f, den);          // MUFU.RCP (<= 2 ulp); forward and backward share these taps
   return bilin_taps(n1x * inv - 1.f, n1y * inv - 1.f, size);
@@ -172,7 +184,8 @@ k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pa
              int size, int kind, float* __restrict__ out) {
   extern __shared__ float A[];
   const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
-  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  prescale(p, size);
   const float* cch = canvas + (size_t)ch * H * W;
   const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
   const int n = size * size;
@@ -343,7 +356,7 @@ k_compose(const float* __restrict__ Ag, const float* __restrict__ table, int siz
   const int ti = blockIdx.x / tiles_x, tj = blockIdx.x - ti * tiles_x;
   const int i = ti * 16 + (threadIdx.x >> 4), j = tj * 16 + (threadIdx.x & 15);
   __shared__ CropParams sp;                      // the crop's parameters are decoded once per CTA
-  if (threadIdx.x == 0) sp = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  if (threadIdx.x == 0) { sp = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS); prescale(sp, size); }
   __syncthreads();
   const CropParams p = sp;
   if (i >= size || j >= size) return;
@@ -472,7 +485,8 @@ k_sample_bwd(const float* __restrict__ grad_out, int H, int W, int pad_top, int 
   extern __shared__ float gA[];
   __shared__ float red[32];
   const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
-  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  prescale(p, size);
   const int n = size * size;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float* go = grad_out + ((size_t)crop * 3 + ch) * n;
@@ -529,7 +543,8 @@ k_sample_bwd_cas(const float* __restrict__ grad_out, int H, int W, int pad_top, 
              int size, int kind, float* __restrict__ grad_canvas, float gscale) {
   extern __shared__ float gA[];
   const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
-  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  prescale(p, size);
   const int n = size * size;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float* go = grad_out + ((size_t)crop * 3 + ch) * n;
@@ -614,7 +629,8 @@ __global__ void __launch_bounds__(1024, 1)
 k_sample_bwd_stage1(const float* __restrict__ grad_out, const float* __restrict__ table, int size, float* __restrict__ gA_out) {
   extern __shared__ float gA[];
   const int crop = blockIdx.x / 3, ch = blockIdx.x - crop * 3;
-  const CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  CropParams p = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  prescale(p, size);
   const int n = size * size;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float* go = grad_out + ((size_t)crop * 3 + ch) * n;
