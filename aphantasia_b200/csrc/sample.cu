@@ -19,6 +19,7 @@
 // (shared atomics), then the bicubic adjoint scatters into the canvas gradient (global red.add).
 #include "aph_common.cuh"
 #include <stdlib.h>
+#include <stdint.h>
 
 namespace aph {
 
@@ -722,6 +723,282 @@ k_sample_bwd_gather(const float* __restrict__ gsrc, float pre_scale_r, float pre
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward, two-kernel form (round 2, default). The one-kernel form above (k_sample_bwd_cas) holds the gradient image of ONE
+// channel in 196 KB of shared memory (one CTA per SM), re-derives the rotate / perspective geometry per channel and accumulates
+// with fp32 shared atomics (compare-and-swap loops): ~420 thread instructions per pixel and channel, issue bound. Here
+//   the adjoint of normalise -> rotate -> erase is a GATHER, 3 channels per thread: the rotate stage is a rigid rotation, so the
+//   output pixels whose bilinear footprint covers source pixel (y, x) lie in the 3 x 3 block around R^T (y, x) (footprint
+//   half-extent |cos| + |sin| <= sqrt 2 < 1.5). No atomics, no shared image;
+//   k_bwd_warp_adjoint : perspective crops only (20 % of the draws): that gather, then the adjoint of the perspective resampling as
+//                        12 global red.add per pixel into a library scratch image gA (kept all-zero between calls: its consumer
+//                        clears what it reads). Crops whose rotate matrix is not a rotation (never drawn by the reference's sampler,
+//                        accepted by the C ABI) take the complete scatter adjoint here;
+//   k_bwd_bicubic3     : bicubic adjoint for all three channels of a (crop, 32-row band): the gradient row chunk comes from the scratch
+//                        (perspective crops), from grad_out directly (angle 0, or no transforms) or from the rotation gather evaluated
+//                        inline (the other 59 %); horizontal taps merge in per-warp strips, which drain to the four source rows as
+//                        16-byte vector reductions (red.global.add.v4.f32). 19 KB of shared memory, 4 CTAs per SM.
+__device__ __forceinline__ bool rigid_rot(const CropParams& p) {
+  const float n0 = p.r00 * p.r00 + p.r10 * p.r10, n1 = p.r01 * p.r01 + p.r11 * p.r11, d = p.r00 * p.r01 + p.r10 * p.r11;
+  return fabsf(n0 - 1.f) < 1e-3f && fabsf(n1 - 1.f) < 1e-3f && fabsf(d) < 1e-3f;
+}
+
+// gradient with respect to B(y, x) (the post-perspective, post-erase image the rotate stage samples) of sum(go * rotate(B)),
+// unnormalised (no 1/std), for the three channels; go = this crop's [3, size, size] block of grad_out
+__device__ __forceinline__ void rot_gather3(const float* __restrict__ go, int n, const CropParams& p, int y, int x, int size, float (&acc)[3]) {
+  const float off = 0.5f * (float)size - 0.5f, fs = (float)size;
+  const float sx = (float)x - off, sy = (float)y - off;
+  // centre of the footprint in output coordinates: the forward samples at R b + off, b = (j, i) - off; R^-1 = R^T
+  const int jr = __float2int_rn(fmaf(p.r00, sx, fmaf(p.r10, sy, off))), ir = __float2int_rn(fmaf(p.r01, sx, fmaf(p.r11, sy, off)));
+  acc[0] = acc[1] = acc[2] = 0.f;
+#pragma unroll
+  for (int di = -1; di <= 1; ++di) {
+    const int i = ir + di;
+    if ((unsigned)i >= (unsigned)size) continue;
+    const float by = (float)i - off;
+    const float cx = fmaf(by, p.r01, off), cy = fmaf(by, p.r11, off);
+#pragma unroll
+    for (int dj = -1; dj <= 1; ++dj) {
+      const int j = jr + dj;
+      if ((unsigned)j >= (unsigned)size) continue;
+      const float bx = (float)j - off;
+      const float ix = fmaf(bx, p.r00, cx), iy = fmaf(bx, p.r10, cy);              // where output pixel (i, j) samples B
+      const float wx = 1.f - fabsf(ix - (float)x), wy = 1.f - fabsf(iy - (float)y);
+      if (wx > 0.f && wy > 0.f) {
+        // coverage of (i, j): sum of its in-bounds tap weights (zeros padding of the [img; ones] stack), separable
+        const float mx = __saturatef(fminf(ix + 1.f, fs - ix)), my = __saturatef(fminf(iy + 1.f, fs - iy));
+        const float w = wx * wy * mx * my;
+        const int o = i * size + j;
+        acc[0] = fmaf(w, __ldg(go + o), acc[0]); acc[1] = fmaf(w, __ldg(go + n + o), acc[1]); acc[2] = fmaf(w, __ldg(go + 2 * n + o), acc[2]);
+      }
+    }
+  }
+}
+
+// crops whose warp stages' adjoint goes through the scratch image (k_bwd_warp_adjoint writes, k_bwd_bicubic3 reads and clears)
+__device__ __forceinline__ bool via_scratch(const CropParams& p) {
+  return (p.flags & APH_FLAG_PERSP) || !(identity_rot(p) || rigid_rot(p));
+}
+
+// adds v[c] * (tap weights of b) into the three channel planes of a [3, size, size] gradient image
+__device__ __forceinline__ void scatter3(float* __restrict__ g, int n, const Bilin& b, int size, const float (&v)[3]) {
+  const int o = b.y0 * size + b.x0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float* gc = g + c * n + o;
+    if (b.w00 != 0.f) atomicAdd(gc, v[c] * b.w00);
+    if (b.w01 != 0.f) atomicAdd(gc + 1, v[c] * b.w01);
+    if (b.w10 != 0.f) atomicAdd(gc + size, v[c] * b.w10);
+    if (b.w11 != 0.f) atomicAdd(gc + size + 1, v[c] * b.w11);
+  }
+}
+
+constexpr int BB_ROWS = 32;     // gradient rows per CTA of k_bwd_bicubic3
+constexpr int WA_ROWS = 8;      // rows per CTA of k_bwd_warp_adjoint (one per warp: the 20 % of crops it serves must still fill the machine)
+
+__global__ void __launch_bounds__(256)
+k_bwd_warp_adjoint(const float* __restrict__ grad_out, const float* __restrict__ table, int size, float gscale, float* __restrict__ gA_all) {
+  const int crop = blockIdx.y;
+  __shared__ CropParams sp;
+  if (threadIdx.x == 0) { sp = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS); prescale(sp, size); }
+  __syncthreads();
+  const CropParams& p = sp;
+  if (!via_scratch(p)) return;
+  const bool persp = (p.flags & APH_FLAG_PERSP) != 0, ident = identity_rot(p), rigid = ident || rigid_rot(p);
+  const int n = size * size, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* go = grad_out + (size_t)crop * 3 * n;
+  float* gA = gA_all + (size_t)crop * 3 * n;
+  const float k0 = c_inv_std[0] * gscale, k1 = c_inv_std[1] * gscale, k2 = c_inv_std[2] * gscale;
+  const int r_end = min(size, ((int)blockIdx.x + 1) * WA_ROWS);
+  for (int y = blockIdx.x * WA_ROWS + warp; y < r_end; y += 8) {
+    for (int x = lane; x < size; x += 32) {
+      const int pix = y * size + x;
+      if (rigid) {
+        // (y, x) = a pixel of B: gather through the rotation, scatter through the perspective taps
+        if (erased(p, y, x)) continue;
+        float v[3];
+        if (ident) { v[0] = __ldg(go + pix); v[1] = __ldg(go + n + pix); v[2] = __ldg(go + 2 * n + pix); }
+        else rot_gather3(go, n, p, y, x, size, v);
+        if (v[0] == 0.f && v[1] == 0.f && v[2] == 0.f) continue;
+        const Bilin b = persp_taps(p, y, x, size);
+        const float m = b.w00 + b.w01 + b.w10 + b.w11;
+        v[0] *= k0 * m; v[1] *= k1 * m; v[2] *= k2 * m;
+        scatter3(gA, n, b, size, v);
+      } else {
+        // (y, x) = an output pixel: the complete scatter adjoint rotate -> erase -> perspective
+        const float g0 = __ldg(go + pix) * k0, g1 = __ldg(go + n + pix) * k1, g2 = __ldg(go + 2 * n + pix) * k2;
+        const Bilin b = rot_taps(p, y, x, size);
+        const float m = b.w00 + b.w01 + b.w10 + b.w11;
+        const float wt[4] = {b.w00, b.w01, b.w10, b.w11};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (wt[t] == 0.f) continue;
+          const int ty = b.y0 + (t >> 1), tx = b.x0 + (t & 1);
+          if (erased(p, ty, tx)) continue;
+          const float gw = wt[t] * m;
+          float v[3] = {g0 * gw, g1 * gw, g2 * gw};
+          if (persp) {
+            const Bilin pb = persp_taps(p, ty, tx, size);
+            const float pm = pb.w00 + pb.w01 + pb.w10 + pb.w11;
+            v[0] *= pm; v[1] *= pm; v[2] *= pm;
+            scatter3(gA, n, pb, size, v);
+          } else {
+            const int o = ty * size + tx;
+            atomicAdd(gA + o, v[0]); atomicAdd(gA + n + o, v[1]); atomicAdd(gA + 2 * n + o, v[2]);
+          }
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// VEC: canvas rows are 16-byte aligned (W % 4 == 0, aligned base, no wrap): strips are anchored at a multiple of 4 canvas columns
+// FIXED: the strips accumulate round(v * 2^k) with the native integer shared atomic instead of the fp32 compare-and-swap loop; k is
+// chosen per 32-pixel chunk from the warp maximum of |g| so that the 24 leading bits of the largest term survive and the sum of the
+// <= 32 x 4 terms of a cell cannot overflow (cells sum <= 48 |g|max: taps have |w| <= 1.2, a clamped border pixel lands <= 1.5).
+template <bool VEC, bool FIXED>
+__global__ void __launch_bounds__(256, 4)
+k_bwd_bicubic3(const float* __restrict__ grad_out, float* __restrict__ gA_all, int H, int W, int pad_top, int pad_left,
+               const float* __restrict__ table, int size, int kind, float gscale, float* __restrict__ grad_canvas) {
+  extern __shared__ __align__(16) float sm[];
+  int* xo_t = reinterpret_cast<int*>(sm);        // [4*size] canvas column of every tap of every gradient column (wrap folded in)
+  float* xw_t = sm + 4 * size;                   // [4*size] their weights
+  __shared__ CropParams sp;
+  const int crop = blockIdx.y;
+  if (threadIdx.x == 0) sp = load_params(table + (size_t)crop * APH_CROP_PARAM_FLOATS);
+  __syncthreads();
+  const CropParams& p = sp;
+  const int n = size * size;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float scale = (size > 1) ? (float)(p.cs - 1) / (float)(size - 1) : 0.f;
+  for (int k = threadIdx.x; k < size; k += blockDim.x) {
+    int idx[4]; float w[4];
+    cubic_taps(k, scale, p.cs, idx, w);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { int x = p.ox + idx[a] - pad_left; x %= W; if (x < 0) x += W; xo_t[4 * k + a] = x; xw_t[4 * k + a] = w[a]; }
+  }
+  float* strip = sm + 8 * size + warp * (3 * STRIP);
+  for (int x = lane; x < 3 * STRIP; x += 32) strip[x] = 0.f;       // re-zeroed as they are drained
+  __syncthreads();
+  // where this crop's gradient rows come from (CTA-uniform)
+  int mode;                                                        // 0: grad_out * pre, 1: + erase mask, 2: rotation gather inline, 3: scratch
+  float pre[3];
+  if (kind != APH_TF_FAST) { mode = 0; for (int c = 0; c < 3; ++c) pre[c] = (kind == APH_TF_NORMALIZE ? c_inv_std[c] : 1.f) * gscale; }
+  else {
+    for (int c = 0; c < 3; ++c) pre[c] = c_inv_std[c] * gscale;
+    if (via_scratch(p)) { mode = 3; pre[0] = pre[1] = pre[2] = 1.f; }
+    else mode = identity_rot(p) ? 1 : 2;
+  }
+  const float* src = grad_out + (size_t)crop * 3 * n;
+  float* scr = gA_all + (size_t)crop * 3 * n;
+  const bool can_strip = (pad_top == 0 && pad_left == 0);
+  const size_t plane = (size_t)H * W;
+  const int r_end = min(size, ((int)blockIdx.x + 1) * BB_ROWS);
+  for (int i = blockIdx.x * BB_ROWS + warp; i < r_end; i += 8) {
+    int yidx[4]; float wya[4]; int yoff[4];
+    cubic_taps(i, scale, p.cs, yidx, wya);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { int y = p.oy + yidx[a] - pad_top; y %= H; if (y < 0) y += H; yoff[a] = y * W; }
+    for (int j0 = 0; j0 < size; j0 += 32) {
+      const int j = j0 + lane;
+      float g[3] = {0.f, 0.f, 0.f};
+      if (j < size) {
+        const int o = i * size + j;
+        if (mode == 3) {
+          g[0] = scr[o]; g[1] = scr[n + o]; g[2] = scr[2 * n + o];
+          if (g[0] != 0.f) scr[o] = 0.f;                           // the scratch image is all-zero again when this kernel is done
+          if (g[1] != 0.f) scr[n + o] = 0.f;
+          if (g[2] != 0.f) scr[2 * n + o] = 0.f;
+        } else if (mode == 2) {
+          if (!erased(p, i, j)) rot_gather3(src, n, p, i, j, size, g);
+        } else if (!(mode == 1 && erased(p, i, j))) {
+          g[0] = __ldg(src + o); g[1] = __ldg(src + n + o); g[2] = __ldg(src + 2 * n + o);
+        }
+        g[0] *= pre[0]; g[1] *= pre[1]; g[2] *= pre[2];
+      }
+      const int jc = min(j, size - 1);
+      const int4 xo = *reinterpret_cast<const int4*>(xo_t + 4 * jc);
+      const float4 wx = *reinterpret_cast<const float4*>(xw_t + 4 * jc);
+      const int xfirst = xo_t[4 * j0], xlast = xo_t[4 * min(j0 + 31, size - 1) + 3];
+      const int xbase = VEC ? (xfirst & ~3) : xfirst;
+      const int span = xlast - xbase + 1;
+      float fs_up = 1.f, fs_dn = 1.f;
+      bool strip_ok = can_strip && span <= STRIP;
+      if (FIXED && strip_ok) {
+        const unsigned mbits = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(fmaxf(fabsf(g[0]), fabsf(g[1])), fabsf(g[2]))));
+        if (mbits == 0u) continue;                                 // nothing in this chunk (warp-uniform)
+        const int E = min(max((int)(mbits >> 23), 25), 254);       // |g| < 2^(E - 126)
+        fs_up = __uint_as_float((unsigned)(278 - E) << 23);        // 2^(151 - E): cell sums stay below 2^31
+        fs_dn = __uint_as_float((unsigned)(E - 24) << 23);         // its inverse
+        if (mbits >= 0x7f800000u) strip_ok = false;                // Inf / NaN upstream: plain fp32 reductions propagate them
+      }
+      if (strip_ok) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (g[c] != 0.f) {
+            if (FIXED) {
+              int* s = reinterpret_cast<int*>(strip) + c * STRIP - xbase;
+              const float gs = g[c] * fs_up;
+              atomicAdd(s + xo.x, __float2int_rn(gs * wx.x)); atomicAdd(s + xo.y, __float2int_rn(gs * wx.y));
+              atomicAdd(s + xo.z, __float2int_rn(gs * wx.z)); atomicAdd(s + xo.w, __float2int_rn(gs * wx.w));
+            } else {
+              float* s = strip + c * STRIP - xbase;
+              atomicAdd(s + xo.x, g[c] * wx.x); atomicAdd(s + xo.y, g[c] * wx.y); atomicAdd(s + xo.z, g[c] * wx.z); atomicAdd(s + xo.w, g[c] * wx.w);
+            }
+          }
+        }
+        __syncwarp();
+        if (VEC) {
+          if (4 * lane < span) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float4* sp4 = reinterpret_cast<float4*>(strip + c * STRIP) + lane;
+              float4 h = *sp4;                                     // (all-zero bits = nothing landed here, in either representation)
+              if (__float_as_uint(h.x) | __float_as_uint(h.y) | __float_as_uint(h.z) | __float_as_uint(h.w)) {
+                *sp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (FIXED) { h.x = (float)__float_as_int(h.x) * fs_dn; h.y = (float)__float_as_int(h.y) * fs_dn; h.z = (float)__float_as_int(h.z) * fs_dn; h.w = (float)__float_as_int(h.w) * fs_dn; }
+                float* gc = grad_canvas + c * plane + xbase + 4 * lane;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) red_add_v4(gc + yoff[a], wya[a] * h.x, wya[a] * h.y, wya[a] * h.z, wya[a] * h.w);
+              }
+            }
+          }
+        } else {
+          for (int x = lane; x < span; x += 32) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float h = strip[c * STRIP + x];
+              if (__float_as_uint(h) != 0u) {
+                strip[c * STRIP + x] = 0.f;
+                if (FIXED) h = (float)__float_as_int(h) * fs_dn;
+                float* gc = grad_canvas + c * plane + xbase + x;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) atomicAdd(gc + yoff[a], wya[a] * h);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (g[c] == 0.f) continue;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            float* r = grad_canvas + c * plane + yoff[a];
+            const float gy = g[c] * wya[a];
+            atomicAdd(r + xo.x, gy * wx.x); atomicAdd(r + xo.y, gy * wx.y); atomicAdd(r + xo.z, gy * wx.z); atomicAdd(r + xo.w, gy * wx.w);
+          }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace aph
 
 using namespace aph;
@@ -798,6 +1075,8 @@ __global__ void __launch_bounds__(256) k_scale_inplace(float* __restrict__ p, si
 }
 }  // namespace aph
 
+static float* g_gW = nullptr;          // warp-stage adjoint scratch [S,3,size,size] of the default backward (all-zero between calls)
+static size_t g_gW_bytes = 0;
 static float* g_gA = nullptr;          // stage-1 scratch [S,3,size,size] (library-owned: survives torch.cuda.empty_cache())
 static size_t g_gA_bytes = 0;
 
@@ -859,6 +1138,45 @@ static int sample_bwd_impl(const float* grad_out, int H, int W, int pad_top, int
   APH_CUDA_OK(cudaMemsetAsync(grad_canvas, 0, (size_t)3 * H * W * sizeof(float), (cudaStream_t)stream));
   if (S == 0) return 0;
   APH_REQUIRE(grad_out && table, "aph_sample_bwd: null pointer");
+  // default: the two-kernel form (k_bwd_warp_adjoint + k_bwd_bicubic3); APH_SAMPLE_BWD_OLD=1 keeps the one-kernel form
+  static int old_bwd = -1;
+  if (old_bwd < 0) { const char* e = getenv("APH_SAMPLE_BWD_OLD"); const char* f = getenv("APH_SAMPLE_BWD_FIXED"); old_bwd = ((e && e[0] == '1') || (f && f[0] == '1')) ? 1 : 0; }
+  if (!old_bwd) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kind == APH_TF_FAST) {
+      const size_t need = (size_t)S * 3 * size * size * sizeof(float);
+      if (need > g_gW_bytes) {
+        APH_CUDA_OK(cudaStreamSynchronize(st));
+        if (g_gW) cudaFree(g_gW);
+        g_gW = nullptr; g_gW_bytes = 0;
+        APH_CUDA_OK(cudaMalloc(&g_gW, need));
+        g_gW_bytes = need;
+        APH_CUDA_OK(cudaMemsetAsync(g_gW, 0, need, st));          // invariant: all-zero between calls (k_bwd_bicubic3 clears what it consumes)
+      }
+      k_bwd_warp_adjoint<<<dim3((size + WA_ROWS - 1) / WA_ROWS, S), 256, 0, st>>>(grad_out, table, size, gscale, g_gW);
+      APH_LAUNCH_OK();
+    }
+    const size_t smem3 = ((size_t)8 * size + 8 * 3 * STRIP) * sizeof(float);
+    static size_t configured3 = 48 * 1024;
+    if (smem3 > configured3) {
+      APH_CUDA_OK((cudaFuncSetAttribute(k_bwd_bicubic3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)));
+      APH_CUDA_OK((cudaFuncSetAttribute(k_bwd_bicubic3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)));
+      APH_CUDA_OK((cudaFuncSetAttribute(k_bwd_bicubic3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)));
+      APH_CUDA_OK((cudaFuncSetAttribute(k_bwd_bicubic3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)));
+      configured3 = smem3;
+    }
+    const bool vec = pad_top == 0 && pad_left == 0 && W % 4 == 0 && ((uintptr_t)grad_canvas & 15) == 0;
+    const dim3 g3((size + BB_ROWS - 1) / BB_ROWS, S);
+    // strips in integer fixed point (native shared atomic add) by default; APH_SAMPLE_STRIP_FP32=1: fp32 strips (compare-and-swap loops)
+    static int fp32_strips = -1;
+    if (fp32_strips < 0) { const char* e = getenv("APH_SAMPLE_STRIP_FP32"); fp32_strips = (e && e[0] == '1') ? 1 : 0; }
+#define APH_BB(V, F) k_bwd_bicubic3<V, F><<<g3, 256, smem3, st>>>(grad_out, g_gW, H, W, pad_top, pad_left, table, size, kind, gscale, grad_canvas)
+    if (vec) { if (fp32_strips) APH_BB(true, false); else APH_BB(true, true); }
+    else { if (fp32_strips) APH_BB(false, false); else APH_BB(false, true); }
+#undef APH_BB
+    APH_LAUNCH_OK();
+    return 0;
+  }
   const size_t smem = ((size_t)size * size + 4 + 16 * (size_t)size + 32 * STRIP) * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {

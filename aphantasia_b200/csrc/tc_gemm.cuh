@@ -359,8 +359,10 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // BN = 384 ("one-wave" tiles for the N = 768 GEMMs: 37 x 2 pair tiles of 256 x 384 on the 74 SM pairs) holds ONE accumulator
   // stage (384 of the 512 TMEM columns); the narrower tiles double-buffer theirs so a tile's epilogue overlaps the next main loop
   constexpr int ACC = (BN == 384) ? 1 : 2;
-  constexpr uint32_t TMEM_COLS = (BN == 384) ? 512 : 2 * BN;
-  static_assert(BN == 128 || BN == 256 || (BN == 384 && CG == 2), "tile widths: 128, 256, or 384 (CTA pair only)");
+  // BN = 192 ("two exact waves" for the N = 768 GEMMs: floor(M/256) x 4 = 148 pair tiles on 74 pairs at M ~ 9500, remainder rows by the
+  // idle epilogue warps) keeps the double buffer: 2 x 192 = 384 columns of a 512-column allocation
+  constexpr uint32_t TMEM_COLS = (BN == 384 || BN == 192) ? 512 : 2 * BN;
+  static_assert(BN == 128 || BN == 256 || ((BN == 384 || BN == 192) && CG == 2), "tile widths: 128, 256, or 192 / 384 (CTA pair only)");
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
@@ -454,7 +456,7 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // groups half, half+2, ... (half = (w-4)/4) of every tile of this CTA.
     const int ew = warp - 4, q = warp & 3, half = ew >> 2;
     const uint32_t ring = smem_u32(smem + L::EPI_OFFSET + ew * (NBUF * EPI_TILE_BYTES));
-    if constexpr (BN == 384 && (EPI == EPI_BF16 || EPI == EPI_BIAS_RESID)) {
+    if constexpr ((BN == 384 || BN == 192) && (EPI == EPI_BF16 || EPI == EPI_BIAS_RESID)) {
       // remainder rows of a one-wave launch: warp tasks spread over all epilogue warps of the grid, done while the main loop runs
       if (epi.tail_m > epi.tail_m0) {
         const int ntasks = (shp.N / 8) * ((epi.tail_m - epi.tail_m0 + 15) / 16);
@@ -504,8 +506,11 @@ k_gemm_bf16_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     } else {
-      constexpr int CW = E::CW, NI = (BN / CW) / 2;             // items (ring tiles of CW accumulator columns) per warp per tile
-      static_assert(NI >= 1, "tile too narrow for the epilogue split");
+      constexpr int CW = E::CW;
+      // items (ring tiles of CW accumulator columns) per warp per tile: column groups half, half+2, ... (an odd group count, BN = 192
+      // with 64-column items, gives the half-0 warps one more)
+      const int NI = (BN / CW - half + 1) / 2;
+      static_assert(BN / CW >= 2, "tile too narrow for the epilogue split");
       uint64_t* my_bar = op_bar + ew * NBUF;
       const int my_tiles = (tile0 < num_tiles) ? (num_tiles - tile0 + tile_step - 1) / tile_step : 0;
       const int total_items = my_tiles * NI;

@@ -85,10 +85,11 @@ static std::atomic<long long> g_variant_launches[4][EPI_KINDS];
 template <int BN, int EPI, int CG>
 static int launch_cfg(const void* A, const void* B, GemmShape shp, const GemmEpi& epi, cudaStream_t st) {
   using E = EpiTraits<EPI>;
-  constexpr int STAGES = (BN == 384) ? 4 : E::STAGES, NBUF = (BN == 384) ? 2 : E::NBUF;      // 384-wide stages are 40 KB
+  // 384-wide stages are 40 KB; 192-wide ones 28 KB (5 stages beside a 2-deep ring, 4 beside a 3-deep one)
+  constexpr int STAGES = (BN == 384) ? 4 : (BN == 192 ? (E::NBUF == 3 ? 4 : 5) : E::STAGES), NBUF = (BN == 384) ? 2 : E::NBUF;
   using L = GemmSmem<BN, STAGES, CG, NBUF>;
   static_assert(L::TOTAL <= 227 * 1024, "GEMM shared-memory budget");
-  g_variant_launches[BN == 384 ? 3 : (CG == 2 ? 2 : (BN == 256 ? 1 : 0))][EPI].fetch_add(1, std::memory_order_relaxed);
+  g_variant_launches[BN == 384 ? 3 : (BN == 192 ? 1 : (CG == 2 ? 2 : 0))][EPI].fetch_add(1, std::memory_order_relaxed);
   static bool configured = false;
   if (!configured) {
     APH_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16_tn<BN, STAGES, EPI, CG, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -139,14 +140,30 @@ int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi,
   // (threshold: from ~40 pair tiles on, one partial round of 256 x 256 pair tiles beats two rounds of 128 x 128 single-CTA tiles, whose
   // A + B operand reads per MMA exceed the shared-memory bandwidth: the N = 768 GEMMs of a 95-crop shard (N = 2 ranks) have 57)
   const bool use_pair = pair && shp.N % 256 == 0 && ((shp.M + 255) / 256) * (shp.N / 256) >= 40;
+  // "two exact waves": N = 768-like shapes whose floor(M/256) x N/192 pair tiles of 256 x 192 fill the 74 SM pairs an integral number of
+  // times where 256-wide tiles leave the last wave half empty (M = 9500, N = 768: 37 x 4 = 148 = 2 x 74 instead of 38 x 3 = 114); the
+  // <= 64 remainder rows are computed inside the same kernel by its epilogue warps on the legacy mma.sync path while the main loop runs.
+  // Kinds: the two the N = 768 GEMMs of the encoder use (bf16 out; +bias +fp32 residual). APH_GEMM_192=0 disables.
+  static int w192 = -1, onewave = -1;
+  if (w192 < 0) { const char* e = getenv("APH_GEMM_192"); w192 = (e && e[0] == '0') ? 0 : 1; }
+  if (onewave < 0) { const char* e = getenv("APH_GEMM_ONEWAVE"); onewave = (e && e[0] == '1') ? 1 : 0; }
+  if (w192 && !onewave && pair && (kind == EPI_BF16 || kind == EPI_BIAS_RESID) && shp.N % 192 == 0 && shp.N % 256 == 0) {
+    const int mt = shp.M / 256, rem = shp.M - mt * 256;
+    const int t192 = mt * (shp.N / 192), t256 = ((shp.M + 255) / 256) * (shp.N / 256), slots = kNumSMs / 2;
+    const int cost192 = ((t192 + slots - 1) / slots) * 192, cost256 = ((t256 + slots - 1) / slots) * 256;
+    if (mt >= 1 && rem <= 64 && t256 >= 40 && cost192 * 100 < cost256 * 88) {       // the narrower instruction reads ~14 % more shared memory per flop
+      GemmShape main_shp{mt * 256, shp.N, shp.K};
+      GemmEpi e2 = epi;
+      e2.tail_a = reinterpret_cast<const bf16*>(A); e2.tail_b = reinterpret_cast<const bf16*>(B); e2.tail_m0 = mt * 256; e2.tail_m = shp.M;
+      return (kind == EPI_BF16) ? launch_cfg<192, EPI_BF16, 2>(A, B, main_shp, e2, st) : launch_cfg<192, EPI_BIAS_RESID, 2>(A, B, main_shp, e2, st);
+    }
+  }
   // "one-wave" tiles: N a multiple of 384 and floor(M/256) * N/384 pair tiles that fit the 74 SM pairs at once (the N = 768 GEMMs of
   // ViT-B at M ~ 9500: 37 x 2 = 74). Two 256-wide waves with the second 54 % full become one; the <= 64 remainder rows are computed
   // inside the same kernel by its epilogue warps (idle during the main loop) on the legacy mma.sync path.
   // MEASURED (profiles/README.md, r2g): not a win -- 165.0 vs 168.1 steps/s at C2. One 384-wide tile per pair has 25 % less main-loop
   // work than two 256-wide rounds but its epilogue is fully exposed, the N = 128 second instruction re-reads A from shared memory and
   // only 4 stages fit. Kept as an opt-in experiment (APH_GEMM_ONEWAVE=1); parity-tested either way.
-  static int onewave = -1;
-  if (onewave < 0) { const char* e = getenv("APH_GEMM_ONEWAVE"); onewave = (e && e[0] == '1') ? 1 : 0; }
   if (onewave && pair && (kind == EPI_BF16 || kind == EPI_BIAS_RESID) && shp.N % 384 == 0) {
     const int mt = shp.M / 256, rem = shp.M - mt * 256, tiles = mt * (shp.N / 384);
     if (mt >= 1 && tiles <= kNumSMs / 2 && 2 * tiles > kNumSMs / 2 && rem <= 64) {
@@ -190,7 +207,7 @@ extern "C" int aph_gemm_epi_test(const void* A, const void* B, int M, int N, int
   return launch_gemm(A, B, GemmShape{M, N, K}, epi, (cudaStream_t)stream);
 }
 
-// launches so far of tile variant `variant` (0: 128x128 single CTA, 1: unused, 2: 256x256 cta_group::2 pair, 3: 256x384 one-wave pair) with
+// launches so far of tile variant `variant` (0: 128x128 single CTA, 1: 256x192 pair (two exact waves), 2: 256x256 cta_group::2 pair, 3: 256x384 one-wave pair) with
 // epilogue kind `epi` (EPI_* order of tc_gemm.cuh: 0 f32, 1 bf16, 2 bias-bf16, 3 bias-gelu, 4 bias-resid, 5 gelugrad, 6 unpatch; -1 = all)
 extern "C" int64_t aph_gemm_variant_launches(int variant, int epi) {
   if (variant < 0 || variant > 3 || epi >= EPI_KINDS) return -1;

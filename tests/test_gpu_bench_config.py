@@ -74,7 +74,7 @@ def test_pair_gemm_epilogue_kinds_at_bench_size(L, kind, M, N, K):
     resid = torch.randn(M, N, device=dev)
     hpre = torch.randn(M, N, device=dev).bfloat16()
     nul = None
-    pair_launches = lambda: lib.aph_gemm_variant_launches(2, EPI[kind]) + lib.aph_gemm_variant_launches(3, EPI[kind])     # 256x256 pair or 256x384 one-wave pair
+    pair_launches = lambda: sum(lib.aph_gemm_variant_launches(v, EPI[kind]) for v in (1, 2, 3))     # 256x192 / 256x256 / 256x384 pair tiles
     before = pair_launches()
     st = L.stream_ptr()
     if kind == 'f32':
@@ -112,6 +112,8 @@ def test_pair_gemm_epilogue_kinds_at_bench_size(L, kind, M, N, K):
     assert pair_launches() == before + 1, 'this shape did not run a cta_group::2 pair kernel'
     if kind in ('bf16', 'bias_resid') and N == 768 and os.environ.get('APH_GEMM_ONEWAVE') == '1':
         assert lib.aph_gemm_variant_launches(3, EPI[kind]) >= 1, 'N = 768 at this M should take the one-wave 256x384 tiles (+ in-kernel remainder rows)'
+    elif kind in ('bf16', 'bias_resid') and N == 768 and os.environ.get('APH_GEMM_192', '1') != '0':
+        assert lib.aph_gemm_variant_launches(1, EPI[kind]) >= 1, 'N = 768 at this M should take the 256x192 pair tiles (two exact waves + in-kernel remainder rows)'
     for got, want, tol in checks:
         assert torch.isfinite(got).all()
         assert _rel(got, want) < tol, (kind, M, N, K, _rel(got, want))
@@ -137,7 +139,7 @@ def test_vit_at_bench_batch_vs_oracle_incl_graph_replay(L, patch, S):
     (eo * cot).sum().backward()
     xc, gc = x.cuda(), cot.cuda()
     emb = torch.empty(S, 512, device='cuda'); gx = torch.empty(S, 3, 224, 224, device='cuda')
-    pairs = lambda: lib.aph_gemm_variant_launches(2, -1) + lib.aph_gemm_variant_launches(3, -1)
+    pairs = lambda: sum(lib.aph_gemm_variant_launches(v, -1) for v in (1, 2, 3))
     pair_before = pairs()
     errs = []
     for it in range(3):

@@ -123,8 +123,9 @@ def test_sampler_vs_reference_golden(L, golden, name):
 
 
 def test_sampler_backward_variants_agree(L):
-    """Backward variants (each in its own process): default = fp32 compare-and-swap shared accumulation; APH_SAMPLE_BWD_FIXED=1 =
-    integer fixed-point shared accumulation; APH_SAMPLE_BWD_GATHER=1 = atomic-free gather. All must agree to fp32 round-off, also
+    """Backward variants (each in its own process): default = three-kernel form (rotation adjoint as a gather, 3 channels per thread);
+    APH_SAMPLE_BWD_OLD=1 = one-kernel form, fp32 compare-and-swap shared accumulation; APH_SAMPLE_BWD_FIXED=1 = one-kernel form, integer
+    fixed-point shared accumulation; APH_SAMPLE_BWD_GATHER=1 = atomic-free tile gather. All must agree to fp32 round-off, also
     for gradients 1e-6 in magnitude (the fixed-point scale is per crop, not absolute)."""
     import os, subprocess, sys
     code = """
@@ -142,11 +143,42 @@ torch.save(c.grad.cpu(), sys.argv[1])
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for mag in ('1.0', '1e-6'):
         outs = []
-        for k, env_add in enumerate((dict(APH_SAMPLE_BWD_FIXED='1'), dict(), dict(APH_SAMPLE_BWD_GATHER='1'))):
+        for k, env_add in enumerate((dict(APH_SAMPLE_BWD_FIXED='1'), dict(), dict(APH_SAMPLE_BWD_GATHER='1'), dict(APH_SAMPLE_BWD_OLD='1'))):
             path = '/tmp/aph_bwd_variant_%d.pt' % k
             subprocess.check_call([sys.executable, '-c', code, path, mag], env=dict(os.environ, **env_add))
             outs.append(torch.load(path))
-        assert _rel(outs[0], outs[1]) < 1e-5 and _rel(outs[2], outs[1]) < 1e-5
+        # the one-kernel variants share the forward's tap arithmetic; the default evaluates the rotation adjoint's weights from the
+        # inverse map (|sample - pixel| hat function): same values to a few ulp of the 224-pixel coordinate
+        assert _rel(outs[0], outs[3]) < 1e-5 and _rel(outs[2], outs[3]) < 1e-5 and _rel(outs[1], outs[3]) < 3e-5
+
+
+def test_sampler_abi_non_rotation_matrix(L):
+    """The C ABI takes any 2x2 inverse affine matrix per crop; the reference's sampler only draws rotations. Rows with a sheared /
+    scaled matrix (with and without a perspective hit) must take the general scatter adjoint, rows with a rotation the gather:
+    forward and backward vs the oracle on a table that mixes both."""
+    from aphantasia_b200 import _rng
+    from aphantasia_b200._lib import check, lib, stream_ptr
+    _seed(21)
+    canvas = torch.rand(1, 3, 300, 420)
+    S, size = 16, 224
+    _seed(9)
+    tabs, frame = _rng.draw_crop_table(S, (300, 420), size, 2, 'uniform', 0.4)
+    tab = tabs[0].copy()
+    for k in range(0, S, 2):                                    # every other crop: not a rotation
+        tab[k, _rng.F_ROT:_rng.F_ROT + 4] = [1.1, 0.25, -0.1, 0.85]
+    assert (tab[:, _rng.F_FLAGS].astype(int) & 1).any(), 'table should contain perspective hits'
+    co = canvas.clone().requires_grad_(True)
+    ref = R.sample_crops(co, tab, size, 2)
+    _seed(6)
+    cot = torch.randn(ref.shape)
+    (ref * cot).sum().backward()
+    x = canvas.cuda().contiguous(); t = torch.tensor(tab).cuda(); out = torch.empty(S, 3, size, size, device='cuda'); g = torch.empty(1, 3, 300, 420, device='cuda')
+    check(lib().aph_sample_fwd(x.data_ptr(), 300, 420, 0, 0, t.data_ptr(), S, size, 2, out.data_ptr(), stream_ptr()), 'fwd')
+    cg = cot.cuda().contiguous()
+    check(lib().aph_sample_bwd(cg.data_ptr(), 300, 420, 0, 0, t.data_ptr(), S, size, 2, g.data_ptr(), stream_ptr()), 'bwd')
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 1e-5
+    assert _rel(g, co.grad) < 1e-4
 
 
 @pytest.mark.parametrize('kind', [0, 1, 2])
