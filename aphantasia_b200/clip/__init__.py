@@ -15,7 +15,7 @@ from collections import OrderedDict
 
 import torch
 
-from .. import _pool, _trace
+from .. import _patchlink, _pool, _trace
 from .._lib import VitConfig, check, lib, require_cuda, stream_ptr
 
 _MODELS = {'ViT-B/32': dict(patch=32, width=768, layers=12, heads=12, out_dim=512, res=224),
@@ -61,14 +61,19 @@ def synthetic_visual_state_dict(patch=32, width=768, layers=12, heads=12, out_di
 
 class _EncodeImage(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, vis):
+    def forward(ctx, x, vis, prepatched=False):
         require_cuda(x, 'encode_image input')
         xi = x.detach().contiguous().float()
         S = xi.shape[0]
         vis._ensure(S)
         emb = _pool.empty((S, vis.output_dim))
         need_bwd = x.requires_grad
-        check(lib().aph_vit_fwd(vis.handle, xi.data_ptr(), S, emb.data_ptr(), int(need_bwd), stream_ptr()), 'aph_vit_fwd')
+        if prepatched:       # the sampler already wrote this batch as the conv1 operand (_patchlink): no k_patchify
+            check(lib().aph_vit_fwd_prepatched(vis.handle, S, emb.data_ptr(), int(need_bwd), stream_ptr()), 'aph_vit_fwd_prepatched')
+            vis.prepatched_forwards += 1
+        else:
+            vis._patch_gen += 1                 # k_patchify overwrites the operand buffer: outstanding stamps are void
+            check(lib().aph_vit_fwd(vis.handle, xi.data_ptr(), S, emb.data_ptr(), int(need_bwd), stream_ptr()), 'aph_vit_fwd')
         _trace.encode()
         ctx.vis, ctx.S, ctx.shape = vis, S, tuple(xi.shape)
         if need_bwd:
@@ -90,12 +95,13 @@ class _EncodeImage(torch.autograd.Function):
         if ctx.generation != vis._generation or ctx.handle_epoch != vis._handle_epoch:
             vis._ensure(ctx.S)
             scratch = torch.empty(ctx.S, vis.output_dim, device=g.device, dtype=torch.float32)
+            vis._patch_gen += 1
             check(lib().aph_vit_fwd(vis.handle, xi.data_ptr(), ctx.S, scratch.data_ptr(), 1, stream_ptr()), 'aph_vit_fwd (recompute)')
             vis._generation += 1            # the arena now belongs to this call; any other pending backward must recompute too
             vis.recomputes += 1
         gi = _pool.empty(ctx.shape)
         check(lib().aph_vit_bwd(vis.handle, g.data_ptr(), ctx.S, gi.data_ptr(), stream_ptr()), 'aph_vit_bwd')
-        return gi, None
+        return gi, None, None
 
 
 class VisionTransformer:
@@ -113,6 +119,8 @@ class VisionTransformer:
         self._sd = {k: v.detach().float().contiguous() for k, v in sd.items()}
         self.handle, self.max_batch = None, 0
         self._generation, self.recomputes, self._handle_epoch = 0, 0, 0        # see _EncodeImage
+        self._patch_gen, self._patch_written, self.prepatched_forwards = 0, False, 0      # see _patchlink
+        _patchlink.register(self)
         if max_batch:
             self._ensure(max_batch)
 
@@ -145,7 +153,7 @@ class VisionTransformer:
             pass
 
     def __call__(self, x):
-        return _EncodeImage.apply(x, self)
+        return _EncodeImage.apply(x, self, _patchlink.matches(x, self))
 
 
 class CLIP:

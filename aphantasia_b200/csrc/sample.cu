@@ -248,10 +248,19 @@ k_sample_fwd(const float* __restrict__ canvas, int H, int W, int pad_top, int pa
 //              without a warp stage.
 //   k_compose: stages 2-5 for ALL THREE channels of a pixel per thread: one evaluation of the rotate (and perspective) taps,
 //              4 (16) gathers per channel from the scratch image through L1.
+// The encoder's patch-embedding GEMM reads its A operand patch-major in bf16: [S*g*g, 3*p*p], row = s*g*g + gy*g + gx,
+// col = c*p*p + py*p + px (conv1 weight layout, vit_ops.cuh k_patchify). With `patches` set the sampler's last stage writes that
+// operand beside the fp32 batch, so the encoder does not re-read 4 bytes per pixel to produce it.
+struct PatchOut { __nv_bfloat16* base; int p, g; };
+__device__ __forceinline__ size_t patch_index(const PatchOut& po, int s, int c, int i, int j) {
+  const int gy = i / po.p, py = i - gy * po.p, gx = j / po.p, px = j - gx * po.p;
+  return ((size_t)(s * po.g + gy) * po.g + gx) * (size_t)(3 * po.p * po.p) + (size_t)(c * po.p + py) * po.p + px;
+}
+
 template <bool WRAP>
 __global__ void __launch_bounds__(256)
 k_resize(const float* __restrict__ canvas, int H, int W, int pad_top, int pad_left, const float* __restrict__ table, int size, int rows_per_cta,
-         int cap, int kind, float* __restrict__ dst) {
+         int cap, int kind, float* __restrict__ dst, PatchOut po) {
   extern __shared__ float rs[];
   int* xi = reinterpret_cast<int*>(rs);              // [4*size] crop-relative source columns of every output column
   float* xw = rs + 4 * size;                         // [4*size] their weights
@@ -306,7 +315,9 @@ k_resize(const float* __restrict__ canvas, int H, int W, int pad_top, int pad_le
       const float4 wx = *reinterpret_cast<const float4*>(xw + 4 * j);
       float acc = wx.x * strip[xo.x];
       acc += wx.y * strip[xo.y]; acc += wx.z * strip[xo.z]; acc += wx.w * strip[xo.w];
-      o[i * size + j] = (kind == APH_TF_FAST) ? acc : fmaf(acc, na, nb);
+      const float v = (kind == APH_TF_FAST) ? acc : fmaf(acc, na, nb);
+      o[i * size + j] = v;
+      if (kind != APH_TF_FAST && po.base) po.base[patch_index(po, crop, ch, i, j)] = __float2bfloat16_rn(v);
     }
     __syncwarp();
   }
@@ -338,7 +349,8 @@ __device__ __forceinline__ void stageB3(const float* __restrict__ A, int n, cons
 }
 
 template <bool PERSP, bool ERASE>
-__device__ __forceinline__ void compose3(const float* __restrict__ A, int n, const CropParams& p, int i, int j, int size, float* __restrict__ o) {
+__device__ __forceinline__ void compose3(const float* __restrict__ A, int n, const CropParams& p, int i, int j, int size, float* __restrict__ o,
+                                         const PatchOut& po, int crop) {
   const Bilin b = rot_taps(p, i, j, size);
   const float mask = b.w00 + b.w01 + b.w10 + b.w11;
   float acc[3] = {0.f, 0.f, 0.f};
@@ -347,12 +359,17 @@ __device__ __forceinline__ void compose3(const float* __restrict__ A, int n, con
   if (b.w10 != 0.f) stageB3<PERSP, ERASE>(A, n, p, b.y0 + 1, b.x0, size, b.w10, acc);
   if (b.w11 != 0.f) stageB3<PERSP, ERASE>(A, n, p, b.y0 + 1, b.x0 + 1, size, b.w11, acc);
   const int pix = i * size + j;
+  const size_t pi = po.base ? patch_index(po, crop, 0, i, j) : 0;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) o[c * n + pix] = fmaf(acc[c] * mask, c_inv_std[c], c_shift[c]);
+  for (int c = 0; c < 3; ++c) {
+    const float v = fmaf(acc[c] * mask, c_inv_std[c], c_shift[c]);
+    o[c * n + pix] = v;
+    if (po.base) po.base[pi + (size_t)c * po.p * po.p] = __float2bfloat16_rn(v);
+  }
 }
 
 __global__ void __launch_bounds__(256)
-k_compose(const float* __restrict__ Ag, const float* __restrict__ table, int size, float* __restrict__ out) {
+k_compose(const float* __restrict__ Ag, const float* __restrict__ table, int size, float* __restrict__ out, PatchOut po) {
   const int crop = blockIdx.y, tiles_x = (size + 15) >> 4;
   const int ti = blockIdx.x / tiles_x, tj = blockIdx.x - ti * tiles_x;
   const int i = ti * 16 + (threadIdx.x >> 4), j = tj * 16 + (threadIdx.x & 15);
@@ -365,15 +382,20 @@ k_compose(const float* __restrict__ Ag, const float* __restrict__ table, int siz
   const float* A = Ag + (size_t)crop * 3 * n;
   float* o = out + (size_t)crop * 3 * n;
   const bool er = (p.flags & APH_FLAG_ERASE) != 0;
-  if (p.flags & APH_FLAG_PERSP) { if (er) compose3<true, true>(A, n, p, i, j, size, o); else compose3<true, false>(A, n, p, i, j, size, o); }
+  if (p.flags & APH_FLAG_PERSP) { if (er) compose3<true, true>(A, n, p, i, j, size, o, po, crop); else compose3<true, false>(A, n, p, i, j, size, o, po, crop); }
   else if (identity_rot(p)) {
     const bool e = erased(p, i, j);
     const int pix = i * size + j;
+    const size_t pi = po.base ? patch_index(po, crop, 0, i, j) : 0;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) o[c * n + pix] = e ? c_shift[c] : fmaf(__ldg(A + c * n + pix), c_inv_std[c], c_shift[c]);
+    for (int c = 0; c < 3; ++c) {
+      const float v = e ? c_shift[c] : fmaf(__ldg(A + c * n + pix), c_inv_std[c], c_shift[c]);
+      o[c * n + pix] = v;
+      if (po.base) po.base[pi + (size_t)c * po.p * po.p] = __float2bfloat16_rn(v);
+    }
   }
-  else if (er) compose3<false, true>(A, n, p, i, j, size, o);
-  else compose3<false, false>(A, n, p, i, j, size, o);
+  else if (er) compose3<false, true>(A, n, p, i, j, size, o, po, crop);
+  else compose3<false, false>(A, n, p, i, j, size, o, po, crop);
 }
 
 // Shared-memory accumulation cell. fp32 atomicAdd on shared memory is a compare-and-swap loop on this architecture
@@ -1013,8 +1035,25 @@ static int check_sample_args(const char* who, int H, int W, int S, int size, int
 static float* g_A = nullptr;           // resized crops [S,3,size,size] between k_resize and k_compose (library-owned scratch)
 static size_t g_A_bytes = 0;
 
+static int sample_fwd_impl(const float* canvas, int H, int W, int pad_top, int pad_left, const float* table, int S,
+                           int size, int kind, float* out, PatchOut po, int* patches_written, void* stream);
+
 extern "C" int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, int pad_left, const float* table, int S,
                               int size, int kind, float* out, void* stream) {
+  return sample_fwd_impl(canvas, H, W, pad_top, pad_left, table, S, size, kind, out, PatchOut{nullptr, 1, 1}, nullptr, stream);
+}
+
+extern "C" int aph_sample_fwd_patches(const float* canvas, int H, int W, int pad_top, int pad_left, const float* table, int S,
+                                      int size, int kind, float* out, void* patches_bf16, int patch, int* patches_written, void* stream) {
+  APH_REQUIRE(patches_bf16 && patches_written, "aph_sample_fwd_patches: null pointer");
+  APH_REQUIRE(patch > 0 && size % patch == 0, "aph_sample_fwd_patches: size=%d is not a multiple of patch=%d", size, patch);
+  *patches_written = 0;
+  return sample_fwd_impl(canvas, H, W, pad_top, pad_left, table, S, size, kind, out,
+                         PatchOut{reinterpret_cast<__nv_bfloat16*>(patches_bf16), patch, size / patch}, patches_written, stream);
+}
+
+static int sample_fwd_impl(const float* canvas, int H, int W, int pad_top, int pad_left, const float* table, int S,
+                           int size, int kind, float* out, PatchOut po, int* patches_written, void* stream) {
   if (int e = check_sample_args("aph_sample_fwd", H, W, S, size, kind)) return e;
   if (S == 0) return 0;
   APH_REQUIRE(canvas && table && out, "aph_sample_fwd: null pointer");
@@ -1047,14 +1086,15 @@ extern "C" int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, in
       }
       const int rows_per_cta = 32;
       const dim3 g1(S * 3, (size + rows_per_cta - 1) / rows_per_cta);
-      if (pad_top || pad_left) k_resize<true><<<g1, 256, smem2, st>>>(canvas, H, W, pad_top, pad_left, table, size, rows_per_cta, cap, kind, dst);
-      else k_resize<false><<<g1, 256, smem2, st>>>(canvas, H, W, pad_top, pad_left, table, size, rows_per_cta, cap, kind, dst);
+      if (pad_top || pad_left) k_resize<true><<<g1, 256, smem2, st>>>(canvas, H, W, pad_top, pad_left, table, size, rows_per_cta, cap, kind, dst, po);
+      else k_resize<false><<<g1, 256, smem2, st>>>(canvas, H, W, pad_top, pad_left, table, size, rows_per_cta, cap, kind, dst, po);
       APH_LAUNCH_OK();
       if (kind == APH_TF_FAST) {
         const int tiles = ((size + 15) / 16) * ((size + 15) / 16);
-        k_compose<<<dim3(tiles, S), 256, 0, st>>>(g_A, table, size, out);
+        k_compose<<<dim3(tiles, S), 256, 0, st>>>(g_A, table, size, out, po);
         APH_LAUNCH_OK();
       }
+      if (patches_written) *patches_written = 1;
       return 0;
     }
   }
@@ -1143,19 +1183,6 @@ static int sample_bwd_impl(const float* grad_out, int H, int W, int pad_top, int
   if (old_bwd < 0) { const char* e = getenv("APH_SAMPLE_BWD_OLD"); const char* f = getenv("APH_SAMPLE_BWD_FIXED"); old_bwd = ((e && e[0] == '1') || (f && f[0] == '1')) ? 1 : 0; }
   if (!old_bwd) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (kind == APH_TF_FAST) {
-      const size_t need = (size_t)S * 3 * size * size * sizeof(float);
-      if (need > g_gW_bytes) {
-        APH_CUDA_OK(cudaStreamSynchronize(st));
-        if (g_gW) cudaFree(g_gW);
-        g_gW = nullptr; g_gW_bytes = 0;
-        APH_CUDA_OK(cudaMalloc(&g_gW, need));
-        g_gW_bytes = need;
-        APH_CUDA_OK(cudaMemsetAsync(g_gW, 0, need, st));          // invariant: all-zero between calls (k_bwd_bicubic3 clears what it consumes)
-      }
-      k_bwd_warp_adjoint<<<dim3((size + WA_ROWS - 1) / WA_ROWS, S), 256, 0, st>>>(grad_out, table, size, gscale, g_gW);
-      APH_LAUNCH_OK();
-    }
     const size_t smem3 = ((size_t)8 * size + 8 * 3 * STRIP) * sizeof(float);
     static size_t configured3 = 48 * 1024;
     if (smem3 > configured3) {
@@ -1170,9 +1197,29 @@ static int sample_bwd_impl(const float* grad_out, int H, int W, int pad_top, int
     // strips in integer fixed point (native shared atomic add) by default; APH_SAMPLE_STRIP_FP32=1: fp32 strips (compare-and-swap loops)
     static int fp32_strips = -1;
     if (fp32_strips < 0) { const char* e = getenv("APH_SAMPLE_STRIP_FP32"); fp32_strips = (e && e[0] == '1') ? 1 : 0; }
-#define APH_BB(V, F) k_bwd_bicubic3<V, F><<<g3, 256, smem3, st>>>(grad_out, g_gW, H, W, pad_top, pad_left, table, size, kind, gscale, grad_canvas)
-    if (vec) { if (fp32_strips) APH_BB(true, false); else APH_BB(true, true); }
-    else { if (fp32_strips) APH_BB(false, false); else APH_BB(false, true); }
+#define APH_BB(V, F, STREAM) k_bwd_bicubic3<V, F><<<g3, 256, smem3, STREAM>>>(grad_out, g_gW, H, W, pad_top, pad_left, table, size, kind, gscale, grad_canvas)
+#define APH_BB_ANY(STREAM)                                                                           \
+    do {                                                                                             \
+      if (vec) { if (fp32_strips) APH_BB(true, false, STREAM); else APH_BB(true, true, STREAM); }    \
+      else { if (fp32_strips) APH_BB(false, false, STREAM); else APH_BB(false, true, STREAM); }      \
+      APH_LAUNCH_OK();                                                                               \
+    } while (0)
+    if (kind != APH_TF_FAST) { APH_BB_ANY(st); return 0; }
+    const size_t need = (size_t)S * 3 * size * size * sizeof(float);
+    if (need > g_gW_bytes) {
+      APH_CUDA_OK(cudaStreamSynchronize(st));
+      if (g_gW) cudaFree(g_gW);
+      g_gW = nullptr; g_gW_bytes = 0;
+      APH_CUDA_OK(cudaMalloc(&g_gW, need));
+      g_gW_bytes = need;
+      APH_CUDA_OK(cudaMemsetAsync(g_gW, 0, need, st));          // invariant: all-zero between calls (k_bwd_bicubic3 clears what it consumes)
+    }
+    const dim3 g1((size + WA_ROWS - 1) / WA_ROWS, S);
+    // (running this chain on a side stream beside the other crops' bicubic adjoint was measured: no gain, 0.335 vs 0.333 ms -- removed)
+    k_bwd_warp_adjoint<<<g1, 256, 0, st>>>(grad_out, table, size, gscale, g_gW);
+    APH_LAUNCH_OK();
+    APH_BB_ANY(st);
+#undef APH_BB_ANY
 #undef APH_BB
     APH_LAUNCH_OK();
     return 0;

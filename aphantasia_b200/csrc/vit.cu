@@ -312,8 +312,30 @@ extern "C" int aph_vit_finalize(aph_vit* vit) {
   return 0;
 }
 
+static int vit_fwd_impl(aph_vit* vit, const float* images, int S, float* emb, int save_for_bwd, void* stream);
+
 extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb, int save_for_bwd, void* stream) {
   APH_REQUIRE(vit && images && emb, "aph_vit_fwd: null argument");
+  return vit_fwd_impl(vit, images, S, emb, save_for_bwd, stream);
+}
+
+// The sampler can write the patch-embedding operand itself (aph_sample_fwd_patches): this is where it goes ...
+extern "C" int aph_vit_patch_operand(aph_vit* vit, int S, void** patches_bf16, int* patch, int* grid) {
+  APH_REQUIRE(vit && patches_bf16 && patch && grid, "aph_vit_patch_operand: null argument");
+  VitImpl* v = reinterpret_cast<VitImpl*>(vit);
+  APH_REQUIRE(v->finalized, "aph_vit_patch_operand: weights not finalized");
+  APH_REQUIRE(S > 0 && S <= v->cfg.max_batch, "aph_vit_patch_operand: S=%d outside (0, max_batch=%d]", S, v->cfg.max_batch);
+  *patches_bf16 = v->patches; *patch = v->cfg.patch; *grid = v->g;
+  return 0;
+}
+
+// ... and the forward that consumes it as it is (no k_patchify: the fp32 images are not read)
+extern "C" int aph_vit_fwd_prepatched(aph_vit* vit, int S, float* emb, int save_for_bwd, void* stream) {
+  APH_REQUIRE(vit && emb, "aph_vit_fwd_prepatched: null argument");
+  return vit_fwd_impl(vit, nullptr, S, emb, save_for_bwd, stream);
+}
+
+static int vit_fwd_impl(aph_vit* vit, const float* images, int S, float* emb, int save_for_bwd, void* stream) {
   VitImpl* v = reinterpret_cast<VitImpl*>(vit);
   APH_REQUIRE(v->finalized, "aph_vit_fwd: weights not finalized");
   APH_REQUIRE(S > 0 && S <= v->cfg.max_batch, "aph_vit_fwd: S=%d outside (0, max_batch=%d]", S, v->cfg.max_batch);
@@ -321,7 +343,7 @@ extern "C" int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb,
   // The only kernels that touch caller-owned memory (k_patchify reads `images`, the last copy writes `emb`) run OUTSIDE the cached
   // graph, so the graph is keyed on the batch size alone: a caller whose tensors move every step (clip_fft.py:285 calls
   // torch.cuda.empty_cache() per step) still replays it.
-  {
+  if (images) {
     const int g = v->g, Mp = S * g * g;
     const size_t n8 = (size_t)Mp * v->Kp / 8;
     APH_CUDA_OK(launch_k(k_patchify, dim3((unsigned)std::min<size_t>((n8 + 255) / 256, (size_t)kNumSMs * 16)), dim3(256), (size_t)0, st, 1, images, v->patches, S, v->cfg.patch, g));

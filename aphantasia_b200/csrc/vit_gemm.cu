@@ -143,9 +143,12 @@ int launch_gemm(const void* A, const void* B, GemmShape shp, const GemmEpi& epi,
   // "two exact waves": N = 768-like shapes whose floor(M/256) x N/192 pair tiles of 256 x 192 fill the 74 SM pairs an integral number of
   // times where 256-wide tiles leave the last wave half empty (M = 9500, N = 768: 37 x 4 = 148 = 2 x 74 instead of 38 x 3 = 114); the
   // <= 64 remainder rows are computed inside the same kernel by its epilogue warps on the legacy mma.sync path while the main loop runs.
-  // Kinds: the two the N = 768 GEMMs of the encoder use (bf16 out; +bias +fp32 residual). APH_GEMM_192=0 disables.
+  // Kinds: the two the N = 768 GEMMs of the encoder use (bf16 out; +bias +fp32 residual).
+  // MEASURED (profiles/README.md, r2m): not a win -- 174.4 vs 176.2 steps/s at C2, the five N = 768 GEMMs within +-3 % of the 256-wide
+  // tiles: an N = 192 instruction needs ~146 B/clk of shared-memory operand reads against 128 available, which eats the 25 % saved
+  // by the exact second wave. Opt-in experiment (APH_GEMM_192=1); parity-tested either way.
   static int w192 = -1, onewave = -1;
-  if (w192 < 0) { const char* e = getenv("APH_GEMM_192"); w192 = (e && e[0] == '0') ? 0 : 1; }
+  if (w192 < 0) { const char* e = getenv("APH_GEMM_192"); w192 = (e && e[0] == '1') ? 1 : 0; }
   if (onewave < 0) { const char* e = getenv("APH_GEMM_ONEWAVE"); onewave = (e && e[0] == '1') ? 1 : 0; }
   if (w192 && !onewave && pair && (kind == EPI_BF16 || kind == EPI_BIAS_RESID) && shp.N % 192 == 0 && shp.N % 256 == 0) {
     const int mt = shp.M / 256, rem = shp.M - mt * 256;

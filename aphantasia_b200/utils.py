@@ -10,7 +10,9 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import _dist, _rng, _trace
+import ctypes as C
+
+from . import _dist, _patchlink, _rng, _trace
 from . import _pool as _tpool
 from ._lib import check, lib, require_cuda, stream_ptr
 
@@ -18,12 +20,22 @@ from ._lib import check, lib, require_cuda, stream_ptr
 # ---------------------------------------------------------------------------------------------- sampler
 class _SliceImgs(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, canvas, table_dev, meta):
+    def forward(ctx, canvas, table_dev, meta, vis=None):
         H, W, pad_top, pad_left, S, size, kind, scale = meta
         x = canvas.detach().contiguous().float()
         out = _tpool.empty((S, 3, size, size))
-        check(lib().aph_sample_fwd(x.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, out.data_ptr(),
-                                   stream_ptr()), 'aph_sample_fwd')
+        if vis is not None and S > 0:
+            # the encoder that will consume this batch takes its patch operand straight from the sampler's last stage (_patchlink)
+            vis._ensure(S)
+            ptr, patch, grid, wrote = C.c_void_p(), C.c_int(), C.c_int(), C.c_int(0)
+            check(lib().aph_vit_patch_operand(vis.handle, S, C.byref(ptr), C.byref(patch), C.byref(grid)), 'aph_vit_patch_operand')
+            check(lib().aph_sample_fwd_patches(x.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, out.data_ptr(),
+                                               ptr, patch.value, C.byref(wrote), stream_ptr()), 'aph_sample_fwd_patches')
+            vis._patch_gen += 1                     # whatever the buffer held before is gone
+            vis._patch_written = bool(wrote.value)
+        else:
+            check(lib().aph_sample_fwd(x.data_ptr(), H, W, pad_top, pad_left, table_dev.data_ptr(), S, size, kind, out.data_ptr(),
+                                       stream_ptr()), 'aph_sample_fwd')
         ctx.meta = meta
         ctx.save_for_backward(table_dev)
         return out
@@ -42,7 +54,7 @@ class _SliceImgs(torch.autograd.Function):
                                           stream_ptr()), 'aph_sample_bwd_scaled')
         if _dist.world() > 1:
             _dist.all_reduce_sum_(gc)
-        return gc, None, None
+        return gc, None, None, None
 
 
 def _transform_kind(transform):
@@ -98,7 +110,12 @@ def slice_imgs(imgs, count, size=224, transform=None, align='uniform', macro=0.)
         local = np.ascontiguousarray(tab[lo:hi])
         tdev = _table_to_device(local, img.device)
         meta = (hw[0], hw[1], pad_top, pad_left, hi - lo, size, kind, float(hi - lo) / float(count))
-        sliced.append(_SliceImgs.apply(img, tdev, meta))
+        vis = _patchlink.target(size) if len(imgs) == 1 else None
+        gen0 = vis._patch_gen if vis is not None else 0
+        out = _SliceImgs.apply(img, tdev, meta, vis)
+        if vis is not None and vis._patch_gen != gen0 and vis._patch_written:
+            _patchlink.stamp(out, vis, hi - lo)
+        sliced.append(out)
     return sliced
 
 

@@ -122,6 +122,11 @@ class DeviceStep:
         self.m = torch.zeros_like(self.params); self.v = torch.zeros_like(self.params)
         self.t = 0
         self.ev = None
+        self.patch_ptr, self.patch, self.wrote = None, 0, C.c_int(0)
+        if os.environ.get('APH_PATCH_FUSE', '1') != '0':
+            ptr, patch, grid = C.c_void_p(), C.c_int(), C.c_int()
+            self.L.check(self.lib.aph_vit_patch_operand(self.vis.handle, S_local, C.byref(ptr), C.byref(patch), C.byref(grid)), 'patch_operand')
+            self.patch_ptr, self.patch = ptr, patch.value
 
     def _mark(self, name):
         if self.ev is not None:
@@ -134,9 +139,15 @@ class DeviceStep:
         ck(lib.aph_synth_fft_fwd(self.gen.plan, self.params.data_ptr(), self.gen.scale.data_ptr(), None, 0, 1.0, self.colmat, 1,
                                  self.x_raw.data_ptr(), self.stats.data_ptr(), self.rgb.data_ptr(), st), 'synth_fwd')
         self._mark('synth_fwd')
-        ck(lib.aph_sample_fwd(self.rgb.data_ptr(), H, W, 0, 0, tab.data_ptr(), self.S, 224, 2, self.crops.data_ptr(), st), 'sample_fwd')
-        self._mark('sample_fwd')
-        ck(lib.aph_vit_fwd(self.vis.handle, self.crops.data_ptr(), self.S, self.emb.data_ptr(), 1, st), 'vit_fwd')
+        if self.patch_ptr is not None:      # the sampler's last stage writes the encoder's bf16 patch operand (no k_patchify)
+            ck(lib.aph_sample_fwd_patches(self.rgb.data_ptr(), H, W, 0, 0, tab.data_ptr(), self.S, 224, 2, self.crops.data_ptr(),
+                                          self.patch_ptr, self.patch, C.byref(self.wrote), st), 'sample_fwd')
+            self._mark('sample_fwd')
+            ck(lib.aph_vit_fwd_prepatched(self.vis.handle, self.S, self.emb.data_ptr(), 1, st), 'vit_fwd')
+        else:
+            ck(lib.aph_sample_fwd(self.rgb.data_ptr(), H, W, 0, 0, tab.data_ptr(), self.S, 224, 2, self.crops.data_ptr(), st), 'sample_fwd')
+            self._mark('sample_fwd')
+            ck(lib.aph_vit_fwd(self.vis.handle, self.crops.data_ptr(), self.S, self.emb.data_ptr(), 1, st), 'vit_fwd')
         self._mark('vit_fwd')
         ck(lib.aph_sim_fwd(self.txt.data_ptr(), 1, self.emb.data_ptr(), self.S, 512, 1, self.loss.data_ptr(), None, self.g_emb.data_ptr(), st), 'sim')
         self.g_emb.mul_(-1.0)                       # loss = -1 * wt * sim (clip_fft.py:116,259)

@@ -115,6 +115,12 @@ int aph_valid_rgb_bwd(const float* grad_out, const float* out, int64_t hw, const
  * out [S,3,size,size]. the resized crop, its tap tables and the per-warp strips must fit one CTA's shared memory (size <= 224).           */
 int aph_sample_fwd(const float* canvas, int H, int W, int pad_top, int pad_left,
                    const float* table, int S, int size, int kind, float* out, void* stream);
+/* Same, and the last stage also writes the batch as the encoder's patch operand (bf16, patch-major: see
+ * aph_vit_patch_operand below); size must be a multiple of patch. *patches_written = 1 when it did (0: the one-kernel
+ * fallback form ran and the caller has to use aph_vit_fwd on `out`).                                 */
+int aph_sample_fwd_patches(const float* canvas, int H, int W, int pad_top, int pad_left,
+                           const float* table, int S, int size, int kind, float* out,
+                           void* patches_bf16, int patch, int* patches_written, void* stream);
 /* grad_out [S,3,size,size] -> grad_canvas [3,H,W] (zeroed here, then accumulated).                 */
 int aph_sample_bwd(const float* grad_out, int H, int W, int pad_top, int pad_left,
                    const float* table, int S, int size, int kind, float* grad_canvas, void* stream);
@@ -158,6 +164,12 @@ int aph_vit_load_tensor(aph_vit* vit, const char* key, const float* data, int64_
 int aph_vit_finalize(aph_vit* vit);
 /* images [S,3,res,res] fp32 (already normalised) -> emb [S,out_dim] fp32. save_for_bwd 0/1.        */
 int aph_vit_fwd(aph_vit* vit, const float* images, int S, float* emb, int save_for_bwd, void* stream);
+/* Patch operand hand-over (the sampler emits the patch-major bf16 A operand of conv1, replacing the
+ * fp32 round trip x.type(dtype) -> conv1's im2col of the reference's clip/model.py VisionTransformer.forward):
+ * aph_vit_patch_operand returns the handle's operand buffer [S*grid*grid, 3*patch*patch] bf16 (row = s*grid*grid + gy*grid + gx,
+ * col = c*patch*patch + py*patch + px) for aph_sample_fwd_patches to fill; aph_vit_fwd_prepatched then runs the forward on it.  */
+int aph_vit_patch_operand(aph_vit* vit, int S, void** patches_bf16, int* patch, int* grid);
+int aph_vit_fwd_prepatched(aph_vit* vit, int S, float* emb, int save_for_bwd, void* stream);
 /* grad_emb [S,out_dim] -> grad_images [S,3,res,res] (overwritten). Uses activations of the last
  * aph_vit_fwd(save_for_bwd=1) with the same S.                                                     */
 int aph_vit_bwd(aph_vit* vit, const float* grad_emb, int S, float* grad_images, void* stream);

@@ -112,7 +112,7 @@ def test_pair_gemm_epilogue_kinds_at_bench_size(L, kind, M, N, K):
     assert pair_launches() == before + 1, 'this shape did not run a cta_group::2 pair kernel'
     if kind in ('bf16', 'bias_resid') and N == 768 and os.environ.get('APH_GEMM_ONEWAVE') == '1':
         assert lib.aph_gemm_variant_launches(3, EPI[kind]) >= 1, 'N = 768 at this M should take the one-wave 256x384 tiles (+ in-kernel remainder rows)'
-    elif kind in ('bf16', 'bias_resid') and N == 768 and os.environ.get('APH_GEMM_192', '1') != '0':
+    elif kind in ('bf16', 'bias_resid') and N == 768 and os.environ.get('APH_GEMM_192') == '1':
         assert lib.aph_gemm_variant_launches(1, EPI[kind]) >= 1, 'N = 768 at this M should take the 256x192 pair tiles (two exact waves + in-kernel remainder rows)'
     for got, want, tol in checks:
         assert torch.isfinite(got).all()
@@ -271,6 +271,78 @@ def test_two_grad_tracked_forwards_before_backward(L):
     (-R.sim_func(txt, o1, 'mix') - 0.5 * R.sim_func(o1, o2, 'mix')).backward()
     assert model.visual.recomputes == 1
     assert _rel(a1.grad, b1.grad) < 2e-2 and _rel(a2.grad, b2.grad) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------- sampler -> encoder patch operand
+@pytest.mark.parametrize('patch', [32, 16])
+def test_sampler_emits_patch_operand_for_the_encoder(L, patch):
+    """slice_imgs' last stage writes the bf16 patch-major conv1 operand into the encoder handle and
+    encode_image on that very tensor skips k_patchify. Same embeddings and canvas gradient, bit for bit, as the plain route
+    (the operand is the same rounding of the same fp32 values); a derived tensor, an in-place edit, a second forward on the stale
+    buffer or two live encoders must take the plain route."""
+    import gc
+    from aphantasia_b200 import _patchlink, transforms
+    from aphantasia_b200.clip import CLIP, synthetic_visual_state_dict
+    from aphantasia_b200.utils import sim_func, slice_imgs
+    gc.collect()
+    lib = L.lib()
+    model = CLIP('ViT-B/%d' % patch, synthetic_visual_state_dict(patch=patch, seed=0), True)
+    vis = model.visual
+    _patchlink._consumers.clear()                 # encoders other tests left alive would (correctly) switch the hand-over off
+    _patchlink.register(vis)
+    _seed(3)
+    canvas = torch.rand(1, 3, 360, 640, device='cuda')
+    txt = torch.randn(1, 512).cuda()
+
+    def run(fuse, kind=transforms.transforms_fast, mutate=None):
+        os.environ['APH_PATCH_FUSE'] = '1' if fuse else '0'
+        c = canvas.clone().requires_grad_(True)
+        _seed(5)
+        n0, f0 = lib.aph_launch_count(), vis.prepatched_forwards
+        crops = slice_imgs([c], 12, 224, kind, 'uniform', 0.4)[0]
+        if mutate:
+            crops = mutate(crops)
+        emb = model.encode_image(crops)
+        n1 = lib.aph_launch_count()
+        (-sim_func(txt, emb, 'mix')).backward()
+        return emb.detach().clone(), c.grad.clone(), n1 - n0, vis.prepatched_forwards - f0
+    try:
+        for _ in range(3):
+            run(False)                                                     # past the encoder's eager / capture steps: launch counts settle
+        e0, g0, n_plain, f_plain = run(False)
+        e1, g1, n_fused, f_fused = run(True)
+        assert f_plain == 0 and f_fused == 1
+        assert torch.equal(e0, e1), 'embeddings differ between the plain and the prepatched route: %g' % _rel(e1, e0)
+        assert _rel(g1, g0) < 1e-5                                         # (the canvas gradient accumulates with atomics: not bit-stable)
+        assert n_fused == n_plain - 1, (n_plain, n_fused)                  # k_patchify is gone, nothing else changed
+        e2, g2, _, f2 = run(True, kind=transforms.normalize())             # the resize kernel emits the operand for kinds without a warp stage
+        e3, g3, _, f3 = run(False, kind=transforms.normalize())
+        assert f2 == 1 and f3 == 0 and torch.equal(e2, e3) and _rel(g2, g3) < 1e-5
+        e4, g4, _, f4 = run(True, mutate=lambda t: t * 1.0)                # a derived tensor carries no stamp
+        assert f4 == 0 and torch.equal(e4, e0)
+        # a second forward of the same batch after another batch went through the encoder: the buffer is stale -> plain route
+        c = canvas.clone()
+        _seed(5)
+        crops = slice_imgs([c], 12, 224, transforms.transforms_fast, 'uniform', 0.4)[0]
+        other = model.encode_image(torch.randn(12, 3, 224, 224, device='cuda'))
+        f0 = vis.prepatched_forwards
+        again = model.encode_image(crops)
+        assert vis.prepatched_forwards == f0 and torch.equal(again, e0) and not torch.equal(other, e0)
+        # in-place edit of the stamped tensor -> version mismatch -> plain route on the edited values
+        _seed(5)
+        crops = slice_imgs([c], 12, 224, transforms.transforms_fast, 'uniform', 0.4)[0]
+        crops.mul_(0.5)
+        f0 = vis.prepatched_forwards
+        half = model.encode_image(crops)
+        assert vis.prepatched_forwards == f0 and not torch.equal(half, e0)
+        # two live encoders (--dualmod): no target
+        model2 = CLIP('ViT-B/16' if patch == 32 else 'ViT-B/32', synthetic_visual_state_dict(patch=48 - patch, seed=0), True)
+        assert _patchlink.target(224) is None
+        del model2
+    finally:
+        os.environ.pop('APH_PATCH_FUSE', None)
+        del model, vis
+        gc.collect()
 
 
 # ---------------------------------------------------------------------------------------------- loss heads, fused Adam (rows f2 / f4)

@@ -179,6 +179,21 @@ def test_sampler_abi_non_rotation_matrix(L):
     torch.cuda.synchronize()
     assert _rel(out, ref) < 1e-5
     assert _rel(g, co.grad) < 1e-4
+    # shard weight of the multi-GPU path (S_local / S, folded into the kernels): scales the gradient, nothing else
+    g2 = torch.empty_like(g)
+    check(lib().aph_sample_bwd_scaled(cg.data_ptr(), 300, 420, 0, 0, t.data_ptr(), S, size, 2, 0.375, g2.data_ptr(), stream_ptr()), 'bwd_scaled')
+    check(lib().aph_sample_bwd(cg.data_ptr(), 300, 420, 0, 0, t.data_ptr(), S, size, 2, g.data_ptr(), stream_ptr()), 'bwd')     # scratch must be clean again
+    torch.cuda.synchronize()
+    assert _rel(g2, 0.375 * co.grad) < 1e-4 and _rel(g, co.grad) < 1e-4
+    # a frame whose rows are not 16-byte aligned takes the scalar-reduction drain
+    Wo = 421
+    canvas_o = torch.rand(1, 3, 300, Wo)
+    co2 = canvas_o.clone().requires_grad_(True)
+    (R.sample_crops(co2, tab, size, 2) * cot).sum().backward()
+    g3 = torch.empty(1, 3, 300, Wo, device='cuda')
+    check(lib().aph_sample_bwd(cg.data_ptr(), 300, Wo, 0, 0, t.data_ptr(), S, size, 2, g3.data_ptr(), stream_ptr()), 'bwd odd W')
+    torch.cuda.synchronize()
+    assert _rel(g3, co2.grad) < 1e-4
 
 
 @pytest.mark.parametrize('kind', [0, 1, 2])
