@@ -133,7 +133,7 @@ def apply_transform_standalone(x, transform):
         tab[0, _rng.F_FLAGS] = _rng.draw_fast(tab[0], h)
     tdev = torch.from_numpy(tab).to(x.device)
     meta = (h, w, 0, 0, 1, h, transform.kind, 1.)
-    return torch.cat([_SliceImgs.apply(x[i:i + 1], tdev, meta) for i in range(n)], 0)
+    return torch.cat([_SliceImgs.apply(x[i:i + 1], tdev, meta, None) for i in range(n)], 0)
 
 
 # ---------------------------------------------------------------------------------------------- loss
