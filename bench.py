@@ -417,7 +417,7 @@ def run_ours(args):
         for ops in (1, 50):
             d = tempfile.mkdtemp(prefix='aph_bench_')
             try:
-                n = max(K, 50)
+                n = max(K, 50) * (2 if ops == 50 else 1)      # opt_step 50: two previews in the window (one made the 50-step leg noisy)
                 for i in range(5):
                     api.script_step(i, ops, d)
                 _drain_saves(); torch.cuda.synchronize()
