@@ -10,13 +10,18 @@
 //   4. rotate (always, even 0 deg): affine grid + the same masked grid_sample (transforms.py:80,
 //      _functional_tensor.py:579-618)
 //   5. (x - mean) / std with the CLIP constants                    (transforms.py:106-108)
-// The stages are SEQUENTIAL resamplings of intermediate size x size images. One CTA owns one
-// (crop, channel): stage 1 is materialised in shared memory (size^2 fp32 = 196 KB at 224), stages 2-5
-// are evaluated by exact tap composition on top of it (rotate tap -> erase test -> perspective taps),
-// so every intermediate is the reference's intermediate and nothing but the packed batch is written.
+// The stages are SEQUENTIAL resamplings of intermediate size x size images; stages 2-5 are evaluated by exact tap composition
+// (rotate tap -> erase test -> perspective taps) on top of the resized crop, so every intermediate is the reference's intermediate.
 //
-// Backward mirrors it: rotate/perspective adjoints scatter into a shared-memory gradient image
-// (shared atomics), then the bicubic adjoint scatters into the canvas gradient (global red.add).
+// Default kernels (round 2):
+//   forward : k_resize (stage 1, separable, into a library scratch image) + k_compose (stages 2-5, three channels per thread; optionally
+//             also the encoder's bf16 patch operand, aph_sample_fwd_patches);
+//   backward: k_bwd_warp_adjoint (perspective crops: rotation adjoint as a gather, perspective adjoint by global reductions into a
+//             scratch image) + k_bwd_bicubic3 (every crop: rotation adjoint gathered inline, bicubic adjoint through per-warp strips
+//             and 16-byte vector reductions into the canvas gradient).
+// The round-1 one-kernel forms (one CTA per (crop, channel), the crop's resized image / gradient image in 196 KB of shared memory:
+// k_sample_fwd, k_sample_bwd_cas, k_sample_bwd) and the atomic-free tile gather stay selectable (APH_SAMPLE_FWD_OLD, APH_SAMPLE_BWD_OLD,
+// APH_SAMPLE_BWD_FIXED, APH_SAMPLE_BWD_GATHER) and are what tests/test_gpu_parity.py::test_sampler_backward_variants_agree compares.
 #include "aph_common.cuh"
 #include <stdlib.h>
 #include <stdint.h>

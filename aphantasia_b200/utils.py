@@ -1,8 +1,8 @@
 """Sampler, loss and helper names -- drop-in for /root/reference/aphantasia/utils.py.
 
 slice_imgs (utils.py:218-254) and sim_func (utils.py:276-295) are the hot-path entry points: the host
-replays the reference's RNG order into a parameter table (_rng.py) and one fused CUDA launch does the rest
-(csrc/sample.cu, csrc/loss.cu). The remaining names are the thin IO helpers clip_fft.py imports.
+replays the reference's RNG order into a parameter table (_rng.py) and two fused CUDA launches each way do the rest
+(csrc/sample.cu; csrc/loss.cu for the loss). The remaining names are the thin IO helpers clip_fft.py imports.
 """
 import os
 

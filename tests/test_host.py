@@ -224,3 +224,52 @@ def test_tabulated_coiflets_have_their_defining_properties(wave, N):
         assert abs(sum(hn[k] * (k - c) ** p for k in range(L))) < 1e-8, 'scaling moment %d' % p
     # PyWavelets relation between the reconstruction pair
     assert np.allclose(g, [(-1) ** k * h[k] for k in range(L)])
+
+
+# ---------------------------------------------------------------------------------------------- sampler -> encoder hand-over (host logic)
+def test_patchlink_stamp_and_match_rules():
+    """aphantasia_b200/_patchlink.py without a GPU: which tensors may take the prepatched encoder route."""
+    import gc
+    import torch
+    from aphantasia_b200 import _patchlink
+
+    class Vis:                       # the attributes _patchlink reads from clip.VisionTransformer
+        def __init__(self, res):
+            self.input_resolution, self._patch_gen, self._handle_epoch = res, 0, 1
+
+    saved = list(_patchlink._consumers)
+    _patchlink._consumers.clear()
+    try:
+        assert _patchlink.target(224) is None                       # no encoder alive
+        v = Vis(224)
+        _patchlink.register(v)
+        assert _patchlink.target(224) is v and _patchlink.target(336) is None
+        os.environ['APH_PATCH_FUSE'] = '0'
+        assert _patchlink.target(224) is None
+        os.environ.pop('APH_PATCH_FUSE')
+        x = torch.zeros(4, 3, 8, 8)
+        assert not _patchlink.matches(x, v)                         # never stamped
+        v._patch_gen = 7
+        _patchlink.stamp(x, v, 4)
+        assert _patchlink.matches(x, v)
+        assert not _patchlink.matches(x * 1.0, v)                   # a derived tensor carries no stamp
+        assert not _patchlink.matches(x, Vis(224))                  # another encoder
+        v._patch_gen = 8                                            # the operand buffer was rewritten since
+        assert not _patchlink.matches(x, v)
+        v._patch_gen = 7
+        v._handle_epoch = 2                                         # the handle was re-created (bigger batch)
+        assert not _patchlink.matches(x, v)
+        v._handle_epoch = 1
+        assert _patchlink.matches(x, v)
+        x.add_(1.0)                                                 # edited in place after the sampler wrote the operand
+        assert not _patchlink.matches(x, v)
+        w = Vis(224)
+        _patchlink.register(w)
+        assert _patchlink.target(224) is None                       # two live encoders (--dualmod): plain route
+        del w
+        gc.collect()
+        assert _patchlink.target(224) is v                          # ... and back once one is gone
+    finally:
+        _patchlink._consumers.clear()
+        for c in saved:
+            _patchlink.register(c)
